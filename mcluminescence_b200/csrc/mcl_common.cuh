@@ -1,0 +1,48 @@
+// mcl_common.cuh -- shared device/host declarations for libmcl_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mcl_b200.h"
+
+namespace mcl {
+
+// Device-side view of one launch: every pointer is device memory.
+struct LaunchParams {
+    const mcl_replica *replicas;
+    const mcl_segment *segments;
+    const double *obs_time;
+    int32_t n_replicas, max_steps;
+    uint64_t seed, replica_id0;
+    // replay
+    const double *replay_u;
+    const int64_t *replay_off;
+    // outputs
+    int32_t *event, *n_e;
+    double *t;
+    int32_t *kind, *e_idx, *h_idx;
+    int32_t *steps_used, *final_n_e;
+    int64_t *esteps, *consumed;
+    int32_t *status;
+    int32_t *obs_n_e;
+    // histogram
+    mcl_hist_spec hist;          // n_bins == 0 => disabled
+    const int32_t *hist_group;   // device [R] or nullptr
+    unsigned long long *hist_events, *hist_occ, *hist_occ_sq;
+    // per-replica scratch: replica r owns [ws + r*ws_stride, +ws_stride)
+    unsigned char *ws;
+    size_t ws_stride;
+    int32_t cap_e, cap_h;        // per-replica element capacities inside the scratch
+};
+
+void set_error(const char *fmt, ...);
+
+// kernels' host launchers (defined in the .cu files)
+cudaError_t launch_replay(const LaunchParams &p, cudaStream_t stream);
+cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int max_slots);
+size_t replay_ws_stride(int cap_e, int cap_h);
+size_t philox_ws_stride(int cap_e, int cap_h);
+int philox_max_slots();       // largest per-replica electron capacity the block kernel supports
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace mcl

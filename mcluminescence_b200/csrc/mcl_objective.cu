@@ -1,0 +1,147 @@
+// mcl_objective.cu -- batched Optimizer objective: S parameter candidates x n_rows lab rows in ONE
+// launch of the native kernel, MSE per candidate back on the host.
+//
+// Replaces, for a whole differential-evolution population at once, the reference chain
+//   optimizer.objective -> cfg_with_params -> run_one_sim -> TLTrapSim.TL_lab / ISO_lab
+//   (src/class/optimizer.py:49-84, src/class/tl_trap_lab.py:27-43,65-123,125-179).
+// Geometry is derived with the reference's own expressions in C doubles (Python's float `**` is
+// C pow), so int() truncations agree with the Python host path.
+#include <cmath>
+#include <vector>
+#include "mcl_common.cuh"
+
+namespace mcl {
+int run_device_args(const mcl_run_args *a);      // mcl_abi.cu
+}
+
+namespace {
+
+// NumPy's float64 add.reduce over a contiguous vector of n < 128 values (pairwise_sum's 8-lane
+// unrolled block), so that the mean matches LabTable.mse() / np.mean bit for bit.
+double numpy_sum(const double *a, size_t n)
+{
+    if (n < 8) { double r = 0.0; for (size_t i = 0; i < n; i++) r += a[i]; return r; }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; j++) r[j] = a[j];
+        size_t i;
+        for (i = 8; i < n - (n % 8); i += 8) for (int j = 0; j < 8; j++) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    }
+    size_t n2 = n / 2; n2 -= n2 % 8;
+    return numpy_sum(a, n2) + numpy_sum(a + n2, n - n2);
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    bool alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess; }
+};
+
+}  // namespace
+
+extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uint64_t seed,
+                             uint64_t candidate_id0, double *mse, int64_t *esteps_total, void *stream)
+{
+    using namespace mcl;
+    if (!P || S <= 0 || !lab || !mse) { set_error("mcl_objective: null argument"); return MCL_ERR_ARG; }
+    if (lab->protocol != MCL_PROTO_TL_LAB && lab->protocol != MCL_PROTO_ISO_LAB) { set_error("mcl_objective: protocol must be TL_LAB or ISO_LAB"); return MCL_ERR_ARG; }
+    if (lab->n_rows <= 0 || !lab->rows || !lab->e_ratio_start || !lab->target) { set_error("mcl_objective: lab table incomplete"); return MCL_ERR_ARG; }
+    const bool iso = lab->protocol == MCL_PROTO_ISO_LAB;
+    if (iso && (!lab->obs_begin || !lab->obs_time)) { set_error("mcl_objective: ISO needs obs_begin / obs_time"); return MCL_ERR_ARG; }
+    const int n_rows = lab->n_rows;
+    const int n_obs = iso ? lab->obs_begin[n_rows] : 0;
+    const size_t R = (size_t)S * (size_t)n_rows;
+    if (R > 0x7fffffffu) { set_error("mcl_objective: too many replicas"); return MCL_ERR_ARG; }
+
+    std::vector<mcl_replica> reps(R);
+    std::vector<mcl_segment> segs(lab->rows, lab->rows + n_rows);
+    for (int k = 0; k < n_rows; k++) {
+        segs[k].dt_cap = 1e20; segs[k].A_opt = 0.0;
+        if (!iso) segs[k].dose_rate = lab->D;                  // tl_trap_lab.py:83
+    }
+    // every candidate re-uses the same observation table; obs outputs are per replica, so the
+    // table is tiled per candidate
+    std::vector<double> obs((size_t)n_obs * (size_t)(iso ? S : 0));
+    for (int c = 0; c < S; c++) {
+        const double rho_prime = P[0 * (size_t)S + c], E_cb = P[1 * (size_t)S + c], E1 = P[2 * (size_t)S + c],
+                     E2 = P[3 * (size_t)S + c], D0 = P[4 * (size_t)S + c], s = P[5 * (size_t)S + c],
+                     b = P[6 * (size_t)S + c], alpha = P[7 * (size_t)S + c], holes = P[8 * (size_t)S + c],
+                     retrap = P[9 * (size_t)S + c];
+        const double rho = rho_prime * (3.0 / (4.0 * M_PI) * pow(alpha, 3.0));     // tl_trap_lab.py:33
+        const double side = pow(holes / rho, 1.0 / 3.0);                              // :34
+        const int n_h0 = (int)(holes * pow(lab->boundary_factor, 3.0));               // engine.py:127
+        for (int k = 0; k < n_rows; k++) {
+            mcl_replica &rp = reps[(size_t)c * n_rows + k];
+            rp.alpha = alpha; rp.b = b; rp.s = s; rp.E_cb = E_cb; rp.E_loc_1 = E1; rp.E_loc_2 = E2;
+            rp.D0 = D0; rp.Retrap = retrap; rp.k_b = lab->k_b; rp.side = side;
+            rp.boundary_factor = lab->boundary_factor;
+            rp.N_e = (int)lab->N_e;
+            rp.n_e0 = (int)(lab->N_e * lab->e_ratio_start[k]);                        // tl_trap_lab.py:38
+            rp.n_h0 = n_h0;
+            rp.protocol = lab->protocol;
+            rp.seg_begin = k; rp.seg_count = 1;
+            rp.obs_begin = iso ? c * n_obs + lab->obs_begin[k] : 0;
+            rp.obs_count = iso ? lab->obs_begin[k + 1] - lab->obs_begin[k] : 0;
+        }
+        if (iso) for (int o = 0; o < n_obs; o++) obs[(size_t)c * n_obs + o] = lab->obs_time[o];
+    }
+
+    DevBuf d_final, d_obs, d_esteps, d_status, d_ws;
+    if (!d_final.alloc(sizeof(int32_t) * R) || !d_esteps.alloc(sizeof(int64_t) * R) || !d_status.alloc(sizeof(int32_t) * R) ||
+        !d_obs.alloc(sizeof(int32_t) * obs.size())) { set_error("mcl_objective: cudaMalloc failed"); return MCL_ERR_ALLOC; }
+    mcl_run_args a;
+    memset(&a, 0, sizeof(a));
+    a.replicas = reps.data(); a.n_replicas = (int32_t)R;
+    a.segments = segs.data(); a.n_segments = n_rows;
+    a.obs_time = iso ? obs.data() : nullptr; a.n_obs = (int32_t)obs.size();
+    a.max_steps = lab->max_steps; a.mode = MCL_MODE_PHILOX;
+    a.seed = seed; a.replica_id0 = candidate_id0 * (uint64_t)n_rows;
+    a.final_n_e = (int32_t *)d_final.p; a.esteps = (int64_t *)d_esteps.p; a.status = (int32_t *)d_status.p;
+    a.obs_n_e = iso ? (int32_t *)d_obs.p : nullptr;
+    a.stream = stream;
+    size_t need = mcl_workspace_bytes(&a);
+    if (!need) return MCL_ERR_ARG;
+    if (!d_ws.alloc(need)) { set_error("mcl_objective: cudaMalloc(workspace %zu) failed", need); return MCL_ERR_ALLOC; }
+    a.workspace = d_ws.p; a.workspace_bytes = need;
+    int rc = mcl_run(&a);
+    if (rc) return rc;
+
+    std::vector<int32_t> final_n(R), status(R), obs_n(obs.size());
+    std::vector<int64_t> est(R);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemcpyAsync(final_n.data(), d_final.p, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(status.data(), d_status.p, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(est.data(), d_esteps.p, sizeof(int64_t) * R, cudaMemcpyDeviceToHost, st);
+    if (iso) cudaMemcpyAsync(obs_n.data(), d_obs.p, sizeof(int32_t) * obs.size(), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("mcl_objective: %s", cudaGetErrorString(e)); return MCL_ERR_CUDA; }
+
+    int64_t total = 0;
+    std::vector<double> se((size_t)(iso ? n_obs : n_rows));
+    for (int c = 0; c < S; c++) {
+        bool failed = false;
+        for (int k = 0; k < n_rows; k++) {
+            size_t r = (size_t)c * n_rows + k;
+            total += est[r];
+            if (status[r] != MCL_OK) failed = true;
+        }
+        if (failed) { mse[c] = INFINITY; continue; }       // a candidate the reference would crash on
+        if (!iso) {
+            for (int k = 0; k < n_rows; k++) {
+                double err = (double)final_n[(size_t)c * n_rows + k] / lab->N_e - lab->target[k];    // tl_trap_lab.py:111
+                se[k] = err * err;
+            }
+        } else {
+            for (int o = 0; o < n_obs; o++) {
+                double err = (double)obs_n[(size_t)c * n_obs + o] / lab->N_e - lab->target[o];      // tl_trap_lab.py:165-167
+                se[o] = err * err;
+            }
+        }
+        mse[c] = numpy_sum(se.data(), se.size()) / (double)se.size();
+    }
+    if (esteps_total) *esteps_total = total;
+    return MCL_OK;
+}

@@ -1,0 +1,651 @@
+// mcl_philox.cu -- native throughput kernel of the trapped-charge kinetics loop (sm_100a).
+//
+// One CTA (NT = 32..512 threads) per replica; one electron per smem slot, two slots per Philox
+// call.  What one step does (reference src/class/simulate.py:51-92, tl_trap_lab.py:90-108):
+//   1. every alive electron i draws a selector and an exponential and forms its waiting time
+//        wait_i = E_i / (k_cb + b*exp(-E_loc/kT - alpha*r_i))          (engine.py:65-77, tl_trap_lab.py:51)
+//      in the log2 domain:  l_i = lg2(-lg2 u_i) - lg2 k_i,  wait_i = ln2 * 2^l_i,
+//      so neither the tunnelling factor (alpha*r up to several hundred) nor E_cb/kT can under/overflow
+//      FP32.  SFU ops per electron-step: lg2, lg2 (+ ex2, lg2 when the conduction-band rate matters);
+//   2. CTA-wide argmin: per-thread running min -> CREDUX.MIN.F32 + ballot per warp -> one smem
+//      row per warp -> ONE __syncthreads -> every warp re-reduces the <=16 rows (double-buffered);
+//   3. dt = min(dt_fill, dt_recomb, dt_cap); fill -> add electron+hole (stale cache semantics of
+//      engine.py:133-152), recombination -> remove the pair and re-search the electrons that
+//      pointed at the dead hole (engine.py:154-175) through a uniform cell grid over the holes;
+//   4. the (event, n_e, t) record is staged in smem and flushed 32 steps at a time with coalesced
+//      stores; optional fused integer histograms of events / occupancy replace the trace for
+//      large ensembles.
+// Random numbers: Philox4x32-10, key = seed (launch-wide round keys live in the constant bank),
+// counter = (slot pair | element index, step, replica id lo, replica id hi | domain).  Results
+// depend only on (seed, global replica id), never on the launch shape or the GPU count.
+//
+// Electron state: cr[slot] = alpha*log2(e)*r (FP32, +inf = empty slot), near[slot] = hole slot, both
+// in shared memory; coordinates (pre-scaled by alpha*log2 e) in the replica's HBM slab and only
+// touched on events.  Holes: [0,n_h0) sorted by grid cell (+cell_start table), [n_h0, ...) fills.
+#include <math_constants.h>
+#include "mcl_common.cuh"
+
+namespace mcl {
+
+namespace {
+
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+constexpr uint32_t DOM_STEP = 0u, DOM_SCALAR = 1u, DOM_SEED_E = 2u, DOM_SEED_H = 3u;
+constexpr float F_INF = __builtin_huge_valf();
+constexpr float DEAD_X = 1e30f;
+constexpr float LN2F = 0.69314718055994530942f;
+constexpr double L2E = 1.4426950408889634074;
+
+struct RoundKeys { uint32_t k[20]; };
+
+struct Cfg {
+    int cap_slots;     // even; smem slots per replica
+    int g_max;         // largest grid edge the slab has room for
+    int cap_cells;     // g_max^3 + 1
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
+                                              const RoundKeys &K)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        unsigned long long p0 = (unsigned long long)PHILOX_M0 * c0;
+        unsigned long long p1 = (unsigned long long)PHILOX_M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k[2 * r];
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k[2 * r + 1];
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+    }
+}
+
+__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float warp_min_f32(float v)
+{
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+// u32 -> uniform on [2^-24, 1 - 2^-24] (exact): one LEA.HI + one FADD, no conversion instruction
+__device__ __forceinline__ float u01(uint32_t r) { return __uint_as_float((r >> 9) | 0x3f800000u) - 0.99999994f; }
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w < v ? w : v;
+    }
+    return v;
+}
+
+struct Holes {
+    float *x, *y, *z;
+    const int *cell_start;
+    int G, n_h0, n_slots;        // n_slots = high-water mark including the fill region
+    float inv_w, w;
+};
+
+// Warp-cooperative nearest alive hole of (x,y,z).  Returns (bits(d2) << 32 | slot) to all lanes.
+__device__ unsigned long long warp_nearest(const Holes &H, float x, float y, float z, int lane)
+{
+    const int G = H.G;
+    int cx = min(G - 1, max(0, (int)(x * H.inv_w)));
+    int cy = min(G - 1, max(0, (int)(y * H.inv_w)));
+    int cz = min(G - 1, max(0, (int)(z * H.inv_w)));
+    unsigned long long best = ~0ull;
+    for (int R = 1;; R++) {
+        const int side = 2 * R + 1, ncb = side * side * side;
+        for (int idx = lane; idx < ncb; idx += 32) {
+            int oz = idx % side - R, oy = (idx / side) % side - R, ox = idx / (side * side) - R;
+            if (R > 1 && max(abs(ox), max(abs(oy), abs(oz))) < R) continue;   // inner block already done
+            int ax = cx + ox, ay = cy + oy, az = cz + oz;
+            if ((unsigned)ax >= (unsigned)G || (unsigned)ay >= (unsigned)G || (unsigned)az >= (unsigned)G) continue;
+            int c = (ax * G + ay) * G + az;
+            int j0 = H.cell_start[c], j1 = H.cell_start[c + 1];
+            for (int j = j0; j < j1; j++) {
+                float dx = x - H.x[j], dy = y - H.y[j], dz = z - H.z[j];
+                float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
+                best = key < best ? key : best;
+            }
+        }
+        best = warp_min_u64(best);
+        // everything outside the scanned block is at least `bound` away
+        float bound = F_INF;
+        bool covered = true;
+        if (cx - R > 0) { bound = fminf(bound, x - (cx - R) * H.w); covered = false; }
+        if (cx + R < G - 1) { bound = fminf(bound, (cx + R + 1) * H.w - x); covered = false; }
+        if (cy - R > 0) { bound = fminf(bound, y - (cy - R) * H.w); covered = false; }
+        if (cy + R < G - 1) { bound = fminf(bound, (cy + R + 1) * H.w - y); covered = false; }
+        if (cz - R > 0) { bound = fminf(bound, z - (cz - R) * H.w); covered = false; }
+        if (cz + R < G - 1) { bound = fminf(bound, (cz + R + 1) * H.w - z); covered = false; }
+        float d2b = __uint_as_float((uint32_t)(best >> 32));
+        if (covered || d2b <= bound * bound) break;
+    }
+    // holes added by fills live outside the grid
+    for (int j = H.n_h0 + lane; j < H.n_slots; j += 32) {
+        float dx = x - H.x[j], dy = y - H.y[j], dz = z - H.z[j];
+        float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
+        best = key < best ? key : best;
+    }
+    return warp_min_u64(best);
+}
+
+template <int NT>
+__device__ __forceinline__ void cta_sync()
+{
+    if (NT > 32) __syncthreads(); else __syncwarp();
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const RoundKeys K, const Cfg cfg)
+{
+    constexpr int NW = NT / 32;
+    const int r = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const mcl_replica rp = p.replicas[r];
+    const unsigned long long rid = p.replica_id0 + (unsigned long long)r;
+    const uint32_t rid_lo = (uint32_t)rid, rid_hi = (uint32_t)(rid >> 32) & 0x0fffffffu;
+
+    // ---------------- shared memory
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *cr = reinterpret_cast<float *>(smem_raw);                  // [cap_slots]
+    int *near = reinterpret_cast<int *>(cr + cfg.cap_slots);          // [cap_slots]
+    __shared__ float red_v[2][32];
+    __shared__ int red_s[2][32];
+    __shared__ uint32_t stepdraw[2][4];
+    __shared__ int rec_ev[32], rec_ne[32];
+    __shared__ double rec_t[32];
+    __shared__ int s_nflag, s_scan[33];
+
+    // ---------------- HBM slab
+    unsigned char *ws = p.ws + (size_t)r * p.ws_stride;
+    const size_t ce = (size_t)p.cap_e, ch = (size_t)p.cap_h;
+    float *ex = reinterpret_cast<float *>(ws), *ey = ex + ce, *ez = ex + 2 * ce;
+    float *hx = ex + 3 * ce, *hy = hx + ch, *hz = hx + 2 * ch;
+    int *hid = reinterpret_cast<int *>(hx + 3 * ch);                  // [cap_h]  init only
+    int *cell_start = hid + ch;                                       // [cap_cells]
+    int *cell_fill = cell_start + cfg.cap_cells;                      // [cap_cells] init only
+    int *flist = cell_fill + cfg.cap_cells;                           // [cap_e]
+
+    int status = MCL_OK;
+    const float core_s = (float)(rp.side * rp.alpha * L2E);
+    const float bnd_s = (float)(rp.side * rp.boundary_factor * rp.alpha * L2E);
+    const int n_h0 = rp.n_h0;
+    int n_e = rp.n_e0;
+    if (n_e > cfg.cap_slots - 2 || n_e > p.cap_e || n_h0 > p.cap_h) status = MCL_ERR_CAPACITY;
+    if (n_e > 0 && n_h0 <= 0) status = MCL_ERR_NOHOLES;
+
+    Holes H;
+    H.x = hx; H.y = hy; H.z = hz; H.cell_start = cell_start; H.n_h0 = n_h0; H.n_slots = n_h0;
+    H.G = max(1, min(cfg.g_max, (int)cbrtf((float)n_h0 * (1.0f / 3.0f))));
+    H.w = bnd_s / (float)H.G; H.inv_w = (float)H.G / bnd_s;
+    const int n_cells = H.G * H.G * H.G;
+
+    for (int s = tid; s < cfg.cap_slots; s += NT) { cr[s] = F_INF; near[s] = -1; }
+    if (tid == 0) s_nflag = 0;
+
+    if (status == MCL_OK) {
+        // ---------------- Box.seed (engine.py:124-129): holes, binned into the cell grid
+        for (int c = tid; c <= n_cells; c += NT) { cell_start[c] = 0; cell_fill[c] = 0; }
+        cta_sync<NT>();
+        auto hole_pos = [&](int j, float &x, float &y, float &z) {
+            uint32_t c0 = (uint32_t)j, c1 = 0u, c2 = rid_lo, c3 = rid_hi | (DOM_SEED_H << 28);
+            philox4x32_10(c0, c1, c2, c3, K);
+            x = u01(c0) * bnd_s; y = u01(c1) * bnd_s; z = u01(c2) * bnd_s;
+        };
+        auto cell_of = [&](float x, float y, float z) {
+            int cx = min(H.G - 1, (int)(x * H.inv_w)), cy = min(H.G - 1, (int)(y * H.inv_w)),
+                cz = min(H.G - 1, (int)(z * H.inv_w));
+            return (cx * H.G + cy) * H.G + cz;
+        };
+        for (int j = tid; j < n_h0; j += NT) {
+            float x, y, z; hole_pos(j, x, y, z);
+            atomicAdd(&cell_fill[cell_of(x, y, z)], 1);
+        }
+        cta_sync<NT>();
+        // exclusive scan of the counts by warp 0 (cell_start[c] = holes in cells < c)
+        if (warp == 0) {
+            int run = 0;
+            for (int base = 0; base < n_cells; base += 32) {
+                int c = base + lane;
+                int v = c < n_cells ? cell_fill[c] : 0;
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                if (c < n_cells) { cell_start[c] = run + inc - v; cell_fill[c] = 0; }
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) cell_start[n_cells] = run;
+        }
+        cta_sync<NT>();
+        for (int j = tid; j < n_h0; j += NT) {
+            float x, y, z; hole_pos(j, x, y, z);
+            int c = cell_of(x, y, z);
+            int q = cell_start[c] + atomicAdd(&cell_fill[c], 1);
+            hx[q] = x; hy[q] = y; hz[q] = z; hid[q] = j;
+        }
+        cta_sync<NT>();
+        // deterministic order inside each cell (by original index): atomics above are unordered
+        for (int c = tid; c < n_cells; c += NT) {
+            int j0 = cell_start[c], j1 = cell_start[c + 1];
+            for (int a = j0 + 1; a < j1; a++) {
+                int id = hid[a]; float x = hx[a], y = hy[a], z = hz[a];
+                int b = a - 1;
+                while (b >= j0 && hid[b] > id) { hid[b + 1] = hid[b]; hx[b + 1] = hx[b]; hy[b + 1] = hy[b]; hz[b + 1] = hz[b]; b--; }
+                hid[b + 1] = id; hx[b + 1] = x; hy[b + 1] = y; hz[b + 1] = z;
+            }
+        }
+        // electrons
+        for (int i = tid; i < n_e; i += NT) {
+            uint32_t c0 = (uint32_t)i, c1 = 0u, c2 = rid_lo, c3 = rid_hi | (DOM_SEED_E << 28);
+            philox4x32_10(c0, c1, c2, c3, K);
+            ex[i] = u01(c0) * core_s; ey[i] = u01(c1) * core_s; ez[i] = u01(c2) * core_s;
+        }
+        cta_sync<NT>();
+        // Box._rebuild (engine.py:113-119): nearest hole of every electron, one warp per electron
+        for (int i = warp; i < n_e; i += NW) {
+            unsigned long long b = warp_nearest(H, ex[i], ey[i], ez[i], lane);
+            if (lane == 0) { cr[i] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[i] = (int)(uint32_t)b; }
+        }
+        cta_sync<NT>();
+    }
+
+    // ---------------- per-replica constants of the rate law, log2 domain
+    const float lb = (float)log2(rp.b), ls = (float)log2(rp.s);
+    const float eb1 = (float)(rp.E_loc_1 * L2E / rp.k_b), eb2 = (float)(rp.E_loc_2 * L2E / rp.k_b);
+    const float ecb = (float)(rp.E_cb * L2E / rp.k_b);
+    // U < Retrap  <=>  r < thr ; Retrap >= 1 / <= 0 handled by collapsing the two channels
+    const bool one_ch_2 = rp.Retrap >= 1.0, one_ch_1 = rp.Retrap <= 0.0;
+    const uint32_t thr = (one_ch_1 || one_ch_2) ? 0u : (uint32_t)(rp.Retrap * 4294967296.0);
+    const float cr_far = bnd_s * 1.7320508f;        // no electron-hole distance exceeds the box diagonal
+
+    const bool lab = rp.protocol != MCL_PROTO_SIMULATE;
+    const bool iso = rp.protocol == MCL_PROTO_ISO_LAB;
+    const double *obs = p.obs_time + rp.obs_begin;
+    int obs_idx = 0;
+    int n_slots = n_e;             // electron slots in use (alive or tombstoned)
+    int n_fill_alive = 0;          // alive holes in the fill region
+    bool ever_filled = false;
+    int rec_i = 0;
+    long long esteps = 0;
+    double t_off = 0.0;
+    const size_t rec_base = (size_t)r * (size_t)p.max_steps;
+    const bool trace = (p.event != nullptr) || (p.n_e != nullptr) || (p.t != nullptr);
+    // histogram
+    const bool hist_on = p.hist.n_bins > 0;
+    const int hgroup = (hist_on && p.hist_group) ? p.hist_group[r] : 0;
+
+    auto flush_records = [&](int count) {       // warp 0 only; count <= 32 records ending at rec_i
+        if (!trace || warp != 0) return;
+        __syncwarp();
+        int first = rec_i - count;
+        if (lane < count) {
+            size_t q = rec_base + (size_t)(first + lane);
+            if (p.event) p.event[q] = rec_ev[lane];
+            if (p.n_e) p.n_e[q] = rec_ne[lane];
+            if (p.t) p.t[q] = rec_t[lane];
+        }
+        __syncwarp();
+    };
+
+    for (int sg = 0; sg < rp.seg_count && status == MCL_OK; sg++) {
+        const mcl_segment S = p.segments[rp.seg_begin + sg];
+        const float dose_over_D0 = (float)(S.dose_rate / rp.D0);
+        const bool dose_on = S.dose_rate != 0.0;
+        const float dt_cap = (float)fmin(S.dt_cap, 3.0e38);
+        const double T0K = S.T_start + 273.15;
+        const float A_opt = lab ? 0.0f : (float)S.A_opt;
+        double t_cur = 0.0;
+        // histogram cursor for this leg
+        const int hrow = hist_on ? (hgroup * rp.seg_count + sg) : 0;
+        int hbin_next = 0;        // next bin whose left edge has not been passed yet
+
+        auto edge = [&](int k) -> double {          // left edge of bin k on the leg's axis, as a time
+            double f = (double)k / (double)p.hist.n_bins;
+            if (p.hist.axis == MCL_AXIS_TIME_LIN) return p.hist.lo + f * (p.hist.hi - p.hist.lo);
+            if (p.hist.axis == MCL_AXIS_TIME_LOG) return exp10(log10(p.hist.lo) + f * (log10(p.hist.hi) - log10(p.hist.lo)));
+            double Tedge = p.hist.lo + f * (p.hist.hi - p.hist.lo);      // deg C
+            return S.T_rate > 0.0 ? (Tedge - S.T_start) / S.T_rate : CUDART_INF;
+        };
+        auto bin_of = [&](double t) -> int {
+            double f;
+            if (p.hist.axis == MCL_AXIS_TIME_LIN) f = (t - p.hist.lo) / (p.hist.hi - p.hist.lo);
+            else if (p.hist.axis == MCL_AXIS_TIME_LOG)
+                f = t > 0.0 ? (log10(t) - log10(p.hist.lo)) / (log10(p.hist.hi) - log10(p.hist.lo)) : -1.0;
+            else f = (S.T_start + S.T_rate * t - p.hist.lo) / (p.hist.hi - p.hist.lo);
+            if (!(f >= 0.0) || !(f < 1.0)) return -1;
+            return min(p.hist.n_bins - 1, (int)(f * p.hist.n_bins));
+        };
+        double hedge_next = hist_on ? edge(0) : CUDART_INF;
+
+        for (;;) {
+            // ---------------- loop condition (simulate.py:51; tl_trap_lab.py:90,147)
+            if (!lab) { if (!(t_cur <= S.duration)) break; }
+            else if (iso) { if (!(obs_idx < rp.obs_count)) break; }
+            else { if (!(t_cur < S.duration)) break; }
+            if (rec_i >= p.max_steps) { status = MCL_ERR_STEPS; break; }
+
+            // ---------------- temperature-dependent scalars (uniform; FP32 from an FP64 clock)
+            const float T_now = (float)((lab && iso) ? T0K : (S.T_start + S.T_rate * t_cur + 273.15));
+            const float invT = __frcp_rn(T_now);
+            float A1 = fmaf(-eb1, invT, lb), A2 = fmaf(-eb2, invT, lb);
+            if (A_opt != 0.0f) {       // (A_opt + b e^{-E/kT}) e^{-alpha r}: fold the sum into the prefactor
+                A1 = lg2_fast(A_opt + ex2_fast(A1));
+                A2 = lg2_fast(A_opt + ex2_fast(A2));
+            }
+            if (one_ch_2) A1 = A2;
+            if (one_ch_1) A2 = A1;
+            const float g = fmaf(-ecb, invT, ls);                       // lg2 k_cb
+            // conduction-band channel can be skipped when it is < 2^-30 of the slowest tunnelling rate
+            const bool has_cb = g > fminf(A1, A2) - cr_far - 30.0f;
+            const int par = rec_i & 1;
+
+            // ---------------- per-electron clocks + running argmin
+            float best = F_INF; int bslot = -1;
+            const int n_pairs = (n_slots + 1) >> 1;
+            const float2 *cr2 = reinterpret_cast<const float2 *>(cr);
+            for (int q = tid; q < n_pairs; q += NT) {
+                const float2 c = cr2[q];
+                uint32_t c0 = (uint32_t)q, c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);
+                philox4x32_10(c0, c1, c2, c3, K);
+                float a0 = ((c0 < thr) ? A2 : A1) - c.x;
+                float a1 = ((c2 < thr) ? A2 : A1) - c.y;
+                float le0 = lg2_fast(-lg2_fast(u01(c1)));
+                float le1 = lg2_fast(-lg2_fast(u01(c3)));
+                float l0, l1;
+                if (has_cb) {
+                    // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
+                    float m0 = fmaxf(a0, g), m1 = fmaxf(a1, g);
+                    float k0 = m0 + lg2_fast(1.0f + ex2_fast(-fabsf(a0 - g)));
+                    float k1 = m1 + lg2_fast(1.0f + ex2_fast(-fabsf(a1 - g)));
+                    l0 = (le0 - k0) + (c.x - c.x);
+                    l1 = (le1 - k1) + (c.y - c.y);
+                } else {
+                    l0 = le0 - a0;
+                    l1 = le1 - a1;
+                }
+                if (l0 < best) { best = l0; bslot = 2 * q; }
+                if (l1 < best) { best = l1; bslot = 2 * q + 1; }
+            }
+            // warp argmin -> one row per warp
+            {
+                float wv = warp_min_f32(best);
+                unsigned m = __ballot_sync(0xffffffffu, best == wv);
+                int src = m ? (__ffs(m) - 1) : 0;
+                int ws_ = __shfl_sync(0xffffffffu, bslot, src);
+                if (lane == 0) { red_v[par][warp] = wv; red_s[par][warp] = ws_; }
+            }
+            if (warp == 0) {
+                // step scalars: fill clock + coordinates of a would-be new electron / hole
+                uint32_t c0 = 0u, c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_SCALAR << 28);
+                philox4x32_10(c0, c1, c2, c3, K);
+                if (lane == 0) {
+                    stepdraw[par][0] = c0; stepdraw[par][1] = c1; stepdraw[par][2] = c2; stepdraw[par][3] = c3;
+                }
+            }
+            cta_sync<NT>();                                   // ===== B1
+            float vmin; int smin;
+            {
+                float v = lane < NW ? red_v[par][lane] : F_INF;
+                int s = lane < NW ? red_s[par][lane] : -1;
+                vmin = warp_min_f32(v);
+                unsigned m = __ballot_sync(0xffffffffu, v == vmin);
+                smin = __shfl_sync(0xffffffffu, s, m ? (__ffs(m) - 1) : 0);
+            }
+            // ---------------- filling clock (tl_trap_lab.py:53-60) and dt (simulate.py:58-60)
+            float dt_fill;
+            {
+                float lam = (n_e == rp.N_e || !dose_on) ? 1e-20f : dose_over_D0 * (float)(rp.N_e - n_e);
+                dt_fill = lam > 0.0f ? (-lg2_fast(u01(stepdraw[par][0])) * LN2F) / lam : 1e20f;
+            }
+            const float dt_rec = n_e > 0 ? ex2_fast(vmin) * LN2F : dt_fill;
+            float dt; bool is_fill, is_rec;
+            if (!lab) {
+                dt = fminf(fminf(dt_fill, dt_rec), dt_cap);
+                is_fill = (dt == dt_fill);
+                is_rec = !is_fill && (dt == dt_rec);
+            } else {
+                is_fill = (dt_fill <= dt_rec);
+                is_rec = !is_fill;
+                dt = is_fill ? dt_fill : dt_rec;
+            }
+            esteps += n_e;
+            const int n_before = n_e;
+            const double t_new = t_cur + (double)dt;
+
+            // ---------------- fused occupancy histogram: edges passed while n_e was n_before
+            if (hist_on && p.hist_occ && hedge_next <= t_new) {
+                while (hbin_next < p.hist.n_bins && hedge_next <= t_new) {
+                    if (tid == 0) {
+                        size_t q = (size_t)hrow * p.hist.n_bins + hbin_next;
+                        atomicAdd(&p.hist_occ[q], (unsigned long long)n_before);
+                        if (p.hist_occ_sq) atomicAdd(&p.hist_occ_sq[q], (unsigned long long)n_before * (unsigned long long)n_before);
+                    }
+                    hbin_next++;
+                    hedge_next = hbin_next < p.hist.n_bins ? edge(hbin_next) : CUDART_INF;
+                }
+            }
+            t_cur = t_new;
+
+            int ev = 0;
+            if (is_rec) {
+                // ---------------- Box.remove_pair (engine.py:154-175)
+                ev = 1;
+                const int h = near[smin];
+                if (tid == ((smin >> 1) % NT)) cr[smin] = F_INF;       // owner of the pair tombstones it
+                n_e--;
+                int h2 = -1;
+                if (ever_filled) {
+                    // stale-cache mode: the reference also refreshes electrons cached on the hole that
+                    // FOLLOWS the removed one in index order (shift-then-mask, engine.py:168-171)
+                    for (int j = h + 1; j < H.n_slots; j++) if (hx[j] < 1e29f) { h2 = j; break; }
+                }
+                if (tid == 0) {
+                    hx[h] = DEAD_X;
+                    if (h >= n_h0) { /* fill-region hole */ }
+                    if (hist_on && p.hist_events) {
+                        int b = bin_of(t_cur);
+                        if (b >= 0) atomicAdd(&p.hist_events[(size_t)hrow * p.hist.n_bins + b], 1ull);
+                    }
+                }
+                if (h >= n_h0) n_fill_alive--;
+                bool mine = false;
+                const int2 *near2 = reinterpret_cast<const int2 *>(near);
+                for (int q = tid; q < n_pairs; q += NT) {
+                    const int2 nn = near2[q];
+                    const float2 c = cr2[q];
+                    if ((nn.x == h || nn.x == h2) && c.x < F_INF) { flist[atomicAdd(&s_nflag, 1)] = 2 * q; mine = true; }
+                    if ((nn.y == h || nn.y == h2) && c.y < F_INF) { flist[atomicAdd(&s_nflag, 1)] = 2 * q + 1; mine = true; }
+                }
+                int any_flag;
+                if (NT > 32) any_flag = __syncthreads_or(mine);       // ===== B2
+                else { __syncwarp(); any_flag = __any_sync(0xffffffffu, mine); }
+                if (any_flag) {
+                    const int nflag = s_nflag;
+                    for (int f = warp; f < nflag; f += NW) {
+                        int s = flist[f];
+                        unsigned long long b = warp_nearest(H, ex[s], ey[s], ez[s], lane);
+                        if (lane == 0) { cr[s] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[s] = (int)(uint32_t)b; }
+                    }
+                    cta_sync<NT>();                           // ===== B3
+                    if (tid == 0) s_nflag = 0;
+                }
+                // ---------------- compaction: keep tombstones below 1/8 of the slots in use
+                if ((n_slots - n_e) * 8 > n_slots && n_slots >= 64) {
+                    cta_sync<NT>();
+                    int run = 0;
+                    for (int base = 0; base < n_slots; base += NT) {
+                        int s = base + tid;
+                        float c = s < n_slots ? cr[s] : F_INF;
+                        int nn = s < n_slots ? near[s] : -1;
+                        bool alive = c < F_INF;
+                        float x = 0.f, y = 0.f, z = 0.f;
+                        if (alive) { x = ex[s]; y = ey[s]; z = ez[s]; }
+                        unsigned m = __ballot_sync(0xffffffffu, alive);
+                        int wpre = __popc(m & ((1u << lane) - 1u));
+                        if (lane == 0) s_scan[warp] = __popc(m);
+                        cta_sync<NT>();
+                        int woff = 0, tot = 0;
+#pragma unroll
+                        for (int k = 0; k < NW; k++) { int v = s_scan[k]; if (k < warp) woff += v; tot += v; }
+                        int dst = run + woff + wpre;
+                        cta_sync<NT>();                       // all reads of this tile done
+                        if (alive) { cr[dst] = c; near[dst] = nn; ex[dst] = x; ey[dst] = y; ez[dst] = z; }
+                        run += tot;
+                    }
+                    cta_sync<NT>();
+                    for (int s = run + tid; s < n_slots; s += NT) { cr[s] = F_INF; near[s] = -1; }
+                    n_slots = run;
+                    cta_sync<NT>();
+                }
+            } else if (is_fill) {
+                // ---------------- Box.add_electron (engine.py:133-152), done by warp 0
+                ever_filled = true;
+                int es = -1;
+                if (n_e == n_slots) es = n_slots;             // no tombstone to reuse
+                const bool append_e = (es >= 0);
+                if (append_e && es >= cfg.cap_slots - 1) { status = MCL_ERR_CAPACITY; break; }
+                const bool append_h = (n_fill_alive == H.n_slots - n_h0);
+                if (append_h && H.n_slots >= p.cap_h) { status = MCL_ERR_CAPACITY; break; }
+                if (warp == 0) {
+                    if (!append_e) {
+                        for (int base = 0; base < n_slots && es < 0; base += 32) {
+                            int s = base + lane;
+                            unsigned m = __ballot_sync(0xffffffffu, s < n_slots && !(cr[s] < F_INF));
+                            if (m) es = base + __ffs(m) - 1;
+                        }
+                    }
+                    int hs = H.n_slots;
+                    if (!append_h) {
+                        hs = -1;
+                        for (int base = n_h0; base < H.n_slots && hs < 0; base += 32) {
+                            int j = base + lane;
+                            unsigned m = __ballot_sync(0xffffffffu, j < H.n_slots && !(hx[j] < 1e29f));
+                            if (m) hs = base + __ffs(m) - 1;
+                        }
+                    }
+                    float nx = u01(stepdraw[par][1]) * core_s, ny = u01(stepdraw[par][2]) * core_s,
+                          nz = u01(stepdraw[par][3]) * core_s;
+                    uint32_t d0 = 1u, d1 = (uint32_t)rec_i, d2 = rid_lo, d3 = rid_hi | (DOM_SCALAR << 28);
+                    philox4x32_10(d0, d1, d2, d3, K);
+                    float qx = u01(d0) * bnd_s, qy = u01(d1) * bnd_s, qz = u01(d2) * bnd_s;
+                    unsigned long long b = warp_nearest(H, nx, ny, nz, lane);     // OLD holes only
+                    if (lane == 0) {
+                        ex[es] = nx; ey[es] = ny; ez[es] = nz;
+                        cr[es] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[es] = (int)(uint32_t)b;
+                        hx[hs] = qx; hy[hs] = qy; hz[hs] = qz;
+                    }
+                }
+                if (append_e) n_slots++;
+                if (append_h) H.n_slots++;
+                n_fill_alive++;
+                n_e++;
+                cta_sync<NT>();
+            }
+
+            // ---------------- record (simulate.py:64,85-89): staged, flushed 32 at a time
+            if (trace && tid == 0) { rec_ev[rec_i & 31] = ev; rec_ne[rec_i & 31] = n_e; rec_t[rec_i & 31] = t_off + t_cur; }
+            rec_i++;
+            if ((rec_i & 31) == 0) flush_records(32);
+            if (iso) {
+                while (obs_idx < rp.obs_count && t_cur >= obs[obs_idx]) {
+                    if (tid == 0 && p.obs_n_e) p.obs_n_e[rp.obs_begin + obs_idx] = n_e;
+                    obs_idx++;
+                }
+            }
+            if (!lab && S.duration != 0.0 && t_cur >= S.duration) break;          // simulate.py:91-92
+        }
+        t_off += t_cur;
+        if (lab) break;
+    }
+    flush_records(rec_i & 31);
+    if (status == MCL_OK && rp.protocol == MCL_PROTO_TL_LAB && rec_i == 0) status = MCL_ERR_NOEVENT;
+    if (tid == 0) {
+        if (p.steps_used) p.steps_used[r] = rec_i;
+        if (p.final_n_e) p.final_n_e[r] = n_e;
+        if (p.esteps) p.esteps[r] = esteps;
+        if (p.consumed) p.consumed[r] = 0;
+        if (p.status) p.status[r] = status;
+    }
+}
+
+// splitmix-style spreading of the user seed into the two Philox key words
+static inline uint64_t mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+}  // namespace
+
+int philox_max_slots() { return 24000; }
+
+static int grid_edge_max(int n_h0_max)
+{
+    int g = (int)floor(cbrt((double)n_h0_max / 3.0)) + 1;
+    return g < 1 ? 1 : g;
+}
+
+struct PhiloxPlan { int nt; int cap_slots; int g_max; int cap_cells; size_t smem; };
+
+static PhiloxPlan make_plan(int cap_e, int n_h0_max, int nt_override)
+{
+    PhiloxPlan pl;
+    pl.cap_slots = (int)align_up((size_t)cap_e + 2, 64);
+    pl.g_max = grid_edge_max(n_h0_max);
+    pl.cap_cells = pl.g_max * pl.g_max * pl.g_max + 1;
+    pl.smem = (size_t)pl.cap_slots * 8;
+    int nt;
+    if (cap_e <= 256) nt = 32;
+    else if (cap_e <= 1024) nt = 64;
+    else if (cap_e <= 4096) nt = 128;
+    else nt = 256;
+    if (nt_override == 32 || nt_override == 64 || nt_override == 128 || nt_override == 256 || nt_override == 512)
+        nt = nt_override;
+    pl.nt = nt;
+    return pl;
+}
+
+static int g_nt_override = 0;
+void philox_set_block_threads(int nt) { g_nt_override = nt; }
+
+size_t philox_ws_stride(int cap_e, int cap_h)
+{
+    // n_h0_max <= cap_h, so sizing the cell tables from cap_h is always enough
+    PhiloxPlan pl = make_plan(cap_e, cap_h, 0);
+    size_t b = sizeof(float) * 3 * ((size_t)cap_e + (size_t)cap_h) + sizeof(int) * ((size_t)cap_h + 2 * (size_t)pl.cap_cells + (size_t)cap_e);
+    return align_up(b, 256);
+}
+
+cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_slots*/)
+{
+    PhiloxPlan pl = make_plan(p.cap_e, p.cap_h, g_nt_override);
+    Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells};
+    RoundKeys K;
+    uint64_t s = mix64(p.seed);
+    uint32_t k0 = (uint32_t)s, k1 = (uint32_t)(s >> 32);
+    for (int r = 0; r < 10; r++) { K.k[2 * r] = k0; K.k[2 * r + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
+    cudaError_t e = cudaSuccess;
+#define MCL_LAUNCH(NT_)                                                                                   \
+    do {                                                                                                  \
+        e = cudaFuncSetAttribute(philox_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem); \
+        if (e != cudaSuccess) return e;                                                                   \
+        philox_kernel<NT_><<<p.n_replicas, NT_, pl.smem, stream>>>(p, K, cfg);                            \
+    } while (0)
+    switch (pl.nt) {
+        case 32: MCL_LAUNCH(32); break;
+        case 64: MCL_LAUNCH(64); break;
+        case 128: MCL_LAUNCH(128); break;
+        case 256: MCL_LAUNCH(256); break;
+        default: MCL_LAUNCH(512); break;
+    }
+#undef MCL_LAUNCH
+    return cudaGetLastError();
+}
+
+}  // namespace mcl

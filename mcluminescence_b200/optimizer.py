@@ -45,3 +45,27 @@ def cfg_with_params(base: Mapping[str, Any], params: np.ndarray):
     cfg.physics_fp.alpha = float(alpha)
     cfg.physics_fp.Retrap = float(retrap)
     return cfg
+
+
+def run_one_sim(cfg: Mapping[str, Any], exp: str, PLOT: bool = False, **kw) -> float:
+    """MSE for one parameter set and one experiment label (reference optimizer.py:68-80)."""
+    from .config import initialize_runs
+    from .tl_trap_lab import TLTrapSim
+    runs = initialize_runs(cfg)
+    for k in ("rng", "seed"):
+        if k in cfg and k not in runs[0]:
+            runs[0][k] = cfg[k]
+    sim = TLTrapSim(runs[0], **kw)
+    if exp == "iso":
+        return sim.ISO_lab("CLBR_IR50_ISO", plot=PLOT)
+    elif exp == "tl_clbr":
+        return sim.TL_lab("CLBR_IRSL50_0.25KperGy", plot=PLOT)
+    elif exp == "tl_fsm-13":
+        return sim.TL_lab("FSM-13_IRSL50_0.25KperGy", plot=PLOT)
+    else:
+        raise ValueError(f"Unknown exp '{exp}'")
+
+
+def objective(p: np.ndarray, cfg: Mapping[str, Any], exp: str, **kw) -> float:
+    """Reference optimizer.py:82-84."""
+    return run_one_sim(cfg_with_params(cfg, p), exp, **kw)

@@ -1,0 +1,146 @@
+"""GPU parity, native Philox mode: ensemble statistics of the FP32/SFU kernel against the CPU
+oracle (float64, MT19937) on the same configurations.
+
+Tolerances (north_star): ensemble means within 3 sigma of the replica spread -- here the combined
+standard error of the two ensembles, with 4 sigma as the hard limit because several quantities
+are checked per case -- plus a two-sample Kolmogorov-Smirnov test on the pooled event times."""
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+R_ENS = 384
+SIGMA = 4.0
+KS_P = 1e-3
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("marked gpu but no CUDA device is visible")
+    from mcluminescence_b200 import _native
+    _native.load()
+    return torch
+
+
+def ensemble_tables(overrides, R):
+    from mcluminescence_b200.config import compose, initialize_runs
+    from mcluminescence_b200.replicas import simulate_tables
+    cfg = compose(overrides=overrides)
+    runs = initialize_runs(cfg)
+    assert len(runs) == 1
+    reps, segs = simulate_tables(runs, R)
+    return reps, segs, int(runs[0]["exp_type_fp"]["steps"])
+
+
+def stats(event, n_e, t, used, grid):
+    """per-replica: events, final n_e, n_e sampled on a time grid; pooled event times."""
+    R = event.shape[0]
+    n_ev = np.array([event[r, :used[r]].sum() for r in range(R)], dtype=np.float64)
+    fin = np.array([n_e[r, used[r] - 1] if used[r] else 0 for r in range(R)], dtype=np.float64)
+    occ = np.zeros((R, len(grid)))
+    times = []
+    for r in range(R):
+        tt, ne = t[r, :used[r]], n_e[r, :used[r]]
+        idx = np.searchsorted(tt, grid, side="right") - 1        # last step at or before the grid time
+        occ[r] = np.where(idx >= 0, ne[np.maximum(idx, 0)], np.nan)
+        times.append(tt[event[r, :used[r]] > 0])
+    return n_ev, fin, occ, np.concatenate(times)
+
+
+def assert_means_agree(a, b, what):
+    se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+    diff = abs(a.mean() - b.mean())
+    assert diff <= SIGMA * se + 1e-12, f"{what}: GPU {a.mean():.4f} vs oracle {b.mean():.4f}, {diff / max(se, 1e-30):.2f} sigma"
+
+
+CASES = {
+    # TL ramp, tunnelling only (the default physics), heavy recombination
+    "tl_ramp": (["exp_type_fp.N_e=200", "exp_type_fp.holes=200", "exp_type_fp.steps=2000",
+                 "exp_type_fp.T_rate=[20]", "exp_type_fp.duration=[40]"], np.linspace(5, 39, 12)),
+    # isothermal, two tunnelling channels
+    "iso_two_channel": (["exp_type_fp.N_e=200", "exp_type_fp.holes=200", "exp_type_fp.steps=2000",
+                         "exp_type_fp.T_start=[250]", "exp_type_fp.T_rate=[0]", "exp_type_fp.duration=[1000]",
+                         "physics_fp.E_loc_2=1.0", "physics_fp.Retrap=0.3"], np.geomspace(1, 900, 12)),
+    # conduction-band channel active (finite E_cb), partially filled
+    "cb_channel": (["physics_fp=lab_TL", "exp_type_fp.N_e=120", "exp_type_fp.holes=150", "exp_type_fp.steps=3000",
+                    "exp_type_fp.T_rate=[2]", "exp_type_fp.duration=[250]", "exp_type_fp.rho_prime=1e-5",
+                    "exp_type_fp.e_ratio_start=0.8"], np.linspace(20, 240, 12)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_simulate_ensemble_matches_oracle(gpu, name):
+    from mcluminescence_b200 import engine
+    from oracle import mcl_oracle as mo
+    overrides, grid = CASES[name]
+    reps, segs, steps = ensemble_tables(overrides, R_ENS)
+    out = engine.run_replicas(reps, segs, steps, seed=20240 + len(name), sync=True)
+    out.raise_on_error()
+    ref = mo.run(reps, segs, steps, seed=77, parallel=True)
+    assert ref.rc == 0
+    g = stats(out.event, out.n_e, out.t, out.steps_used, grid)
+    o = stats(ref.event, ref.n_e, ref.t, ref.steps_used, grid)
+    assert_means_agree(g[0], o[0], f"{name}: events per replica")
+    assert_means_agree(g[1], o[1], f"{name}: final n_e")
+    for k in range(len(grid)):
+        assert_means_agree(g[2][:, k], o[2][:, k], f"{name}: n_e(t={grid[k]:.3g})")
+    from scipy.stats import ks_2samp
+    ks = ks_2samp(g[3], o[3])
+    assert ks.pvalue > KS_P, f"{name}: KS on event times p={ks.pvalue:.2e} (D={ks.statistic:.4f})"
+    # bookkeeping identities of the kernel's own outputs
+    est = np.array([(out.n_e[r, :out.steps_used[r]] + out.event[r, :out.steps_used[r]]).sum()
+                    for r in range(R_ENS)])
+    assert np.array_equal(est, out.esteps)              # no fills here: n_before = n_after + event
+
+
+def test_results_depend_only_on_seed_and_global_replica_id(gpu):
+    """Sharding invariance: replica g gives the same trace whatever batch / offset it ran in."""
+    from mcluminescence_b200 import engine
+    reps, segs, steps = ensemble_tables(CASES["tl_ramp"][0], 24)
+    full = engine.run_replicas(reps, segs, steps, seed=5, sync=True)
+    part = engine.run_replicas(reps[8:16], segs, steps, seed=5, replica_id0=8, sync=True)
+    assert np.array_equal(full.event[8:16], part.event)
+    assert np.array_equal(full.n_e[8:16], part.n_e)
+    assert np.array_equal(full.t[8:16], part.t)
+    other = engine.run_replicas(reps[8:16], segs, steps, seed=6, replica_id0=8, sync=True)
+    assert not np.array_equal(other.event, part.event)
+
+
+@pytest.mark.parametrize("exp", ["tl_clbr", "iso"])
+def test_lab_protocol_ensemble_matches_oracle(gpu, exp):
+    """TL_lab / ISO_lab with fills, stale caches and the conduction-band channel."""
+    from mcluminescence_b200 import engine
+    from mcluminescence_b200.config import compose, initialize_runs
+    from mcluminescence_b200.replicas import LAB_CSV, LabTable
+    from oracle import mcl_oracle as mo
+    cfg = compose(overrides=helpers.LAB_OVERRIDES)
+    run = initialize_runs(cfg)[0]
+    csv, proto = LAB_CSV[exp]
+    lt = LabTable(csv, proto, helpers.DATA_ROOT)
+    reps1, segs = lt.tables(run)
+    n_rows, M = len(reps1), 96
+    reps = np.tile(reps1, M)
+    obs_time = np.tile(lt.obs_time, M)
+    if proto == 2:
+        n_obs = len(lt.obs_time)
+        for m in range(M):
+            reps["obs_begin"][m * n_rows:(m + 1) * n_rows] += m * n_obs
+    steps = int(run["exp_type_fp"]["steps"])
+    out = engine.run_replicas(reps, segs, steps, seed=99, obs_time=obs_time, trace=False, sync=True)
+    out.raise_on_error()
+    ref = mo.run(reps, segs, steps, seed=1234, obs_time=obs_time, parallel=True, trace=False)
+    assert ref.rc == 0
+    if proto == 1:
+        g = out.final_n_e.reshape(M, n_rows).astype(float)
+        o = ref.final_n_e.reshape(M, n_rows).astype(float)
+    else:
+        g = out.obs_n_e.reshape(M, -1).astype(float)
+        o = ref.obs_n_e.reshape(M, -1).astype(float)
+    for k in range(g.shape[1]):
+        assert_means_agree(g[:, k], o[:, k], f"{exp}: column {k}")
+    ge, oe = out.esteps.reshape(M, n_rows).sum(1).astype(float), ref.esteps.reshape(M, n_rows).sum(1).astype(float)
+    assert_means_agree(ge, oe, f"{exp}: electron-steps per objective")
