@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- electron-steps/s of the trapped-charge kinetics hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c5|c1] [--replicas R]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # CPU arm: the oracle port on all host threads
+
+One "step" = one pass of the hot path over one batch of replicas (seed the boxes, run every
+replica's schedule to the end, fuse the ensemble histograms, all-reduce them across ranks).
+Workload at every N: BASELINE.json configs[1] (C2) -- isothermal hold then optical readout,
+N_e = 10^4 electrons per replica, `--replicas` replicas PER GPU (weak scaling; global replica ids are
+offset by rank so every replica of the job is distinct).
+
+Prints ONE JSON line (rank 0).  `value` = electron-steps of all ranks / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "electron-steps/sec (device-timed)"
+UNIT = "electron-steps/s"
+
+# Algorithmic cost of one electron-step: 3 SFU ops + 45 FP32/INT32 lane-ops
+SFU_PER_ESTEP = 3.0
+LANEOPS_PER_ESTEP = 45.0
+
+
+def build_workload(name: str, replicas: int):
+    from mcluminescence_b200 import workloads
+    if name == "c2":
+        return workloads.c2(n_replicas=replicas)
+    if name == "c5":
+        return workloads.c5(n_replicas=replicas)
+    if name == "c1":
+        return workloads.c1()
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_leg(workload_name: str, threads: int, n_replicas: int, seed: int):
+    """Time the CPU oracle (the C restatement of the reference's algorithm) on a bounded sample
+    of the SAME replica shape.  Returns (electron-steps/s, electron-steps, seconds)."""
+    from oracle import mcl_oracle as mo
+    wl = build_workload(workload_name, n_replicas)
+    reps = wl["replicas"][:n_replicas]
+    t0 = time.perf_counter()
+    res = mo.run(reps, wl["segments"], wl["max_steps"], seed=seed, parallel=True, threads=threads, trace=False)
+    dt = time.perf_counter() - t0
+    if res.rc != 0:
+        raise RuntimeError(f"oracle failed with status {res.rc}")
+    es = int(res.esteps.sum())
+    return es / dt, es, dt
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own algorithm on the host cores (the oracle port; the
+    NumPy reference itself cannot travel to the GPU box), all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import mcl_oracle as mo
+    threads = mo.max_threads()
+    n_rep = max(threads, 1)
+    vals, es_tot, secs = [], 0, 0.0
+    for i in range(args.warmup + args.steps):
+        v, es, dt = cpu_leg(args.workload, threads, n_rep, seed=1000 + i)
+        if i >= args.warmup:
+            vals.append(v); es_tot += es; secs += dt
+    value = es_tot / secs
+    sample = (f"{n_rep} replicas of the {args.workload.upper()} replica shape per step "
+              f"(one per host thread), {args.steps} steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": build_workload(args.workload, 1)["name"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c1"])
+    ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU per step (0 = workload default)")
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.replicas <= 0:
+        args.replicas = {"c2": 10_000, "c5": 6_250, "c1": 8}[args.workload]
+
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mcluminescence_b200 import engine, ensemble
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+
+    wl = build_workload(args.workload, args.replicas)
+    peaks = engine.device_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i):
+        # every step is a fresh ensemble: new Philox seed, same shapes
+        finish, T = ensemble.run_ensemble(wl, seed=args.seed + 7919 * i, rank=rank, world=world,
+                                          shard=False)
+        return finish, T
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    stream = torch.cuda.current_stream()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    counters = []
+    wall0 = time.perf_counter()
+    e_first, e_last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_first.record(stream)
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        finish, T = one_step(args.warmup + i)
+        ev[i][1].record(stream)
+        counters.append(T["counters"])
+    e_last.record(stream)
+    barrier()
+    wall1 = time.perf_counter()
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+
+    total_ms = e_first.elapsed_time(e_last)
+    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    # counters were all-reduced inside the step: esteps is already the whole-job count
+    esteps_job = int(sum(int(c[0].item()) for c in counters))
+    errors = int(sum(int(c[2].item()) for c in counters))
+    t_ms = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    max_ms = float(t_ms.item())
+    value = esteps_job / (max_ms * 1e-3)
+
+    # ---- e2e: the public API with HOST tables in and HOST results out, wall-clocked
+    barrier()
+    t0 = time.perf_counter()
+    e2e_es = 0
+    for i in range(args.steps):
+        finish, T = one_step(1000 + i)
+        res = finish()                      # D2H of histograms + counters, synchronises
+        e2e_es += res.esteps
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_es / float(e2e_t.item())
+    hist = wl["hist"]
+    h2d = int(wl["replicas"].nbytes + wl["segments"].nbytes)
+    d2h = int((3 * hist.n_groups * hist.n_bins * 8 if hist is not None else 0) + 4 * 8)
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (philox_kernel: one launch per step)
+        n_sm = peaks["n_sm"]
+        per_launch_es = esteps_job / max(args.steps, 1) / world
+        kern_s = statistics.mean(kernel_ms) * 1e-3
+        achieved = per_launch_es / kern_s
+        sm_hz = (clocks["sm_mhz"] or peaks["sm_clock_mhz"]) * 1e6
+        peak_measured = min(peaks["mufu_gops"] * 1e9 / SFU_PER_ESTEP, peaks["ffma_gops"] * 1e9 / LANEOPS_PER_ESTEP)
+        peak_nominal = n_sm * 1.965e9 / max(SFU_PER_ESTEP / 16.0, LANEOPS_PER_ESTEP / 128.0)
+        steps_job = int(sum(int(c[1].item()) for c in counters))
+        hbm_bytes = 16.0 * steps_job / world / max(args.steps, 1)      # 16 B per (replica, step) record
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            hbm_peak, hbm_src = float(mp["hbm_gbs"]), "measured"
+        except Exception:  # noqa: BLE001
+            hbm_peak, hbm_src = 6650.0, "fallback"
+        roofline = {
+            "bound": "sfu_fp32_issue", "achieved": achieved, "peak": peak_measured, "unit": UNIT,
+            "frac": achieved / peak_measured, "traffic": None,
+            "kernel": "philox_kernel", "model": f"{SFU_PER_ESTEP:g} SFU + {LANEOPS_PER_ESTEP:g} FP32/INT32 lane-ops per electron-step",
+            "peak_source": "mcl_device_peaks microbenchmarks in this run (MUFU, FFMA issue)",
+            "peak_nominal": peak_nominal, "frac_nominal": achieved / peak_nominal,
+            "pipe_peaks_gops": {k: peaks[k] for k in ("mufu_gops", "ffma_gops", "imad_gops", "lop3_gops")},
+            "sm_mhz_during": sm_hz / 1e6,
+            "hbm": {"achieved_gbs": hbm_bytes / kern_s / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                    "frac": hbm_bytes / kern_s / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": hbm_bytes},
+        }
+        cpu = None
+        if not args.no_cpu:
+            from oracle import mcl_oracle as mo
+            threads = mo.max_threads()
+            v, es, dt = cpu_leg(args.workload, threads, max(threads, 1), seed=4242)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{max(threads, 1)} replicas of the same replica shape, one per host thread, {dt:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": max_ms / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "replicas_per_gpu_per_step": int(len(wl["replicas"])),
+                       "l2": "working set per step (replica slabs) exceeds the 126 MB L2; fresh seed every step",
+                       "rng": "philox4x32-10", "errors": errors},
+            "clocks": clocks, "gpu_launches": args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -197,6 +197,9 @@ class ReplayStream:
         end = self.pos + n
         have = self._base + self._buf.size
         if end > have:
+            if self.pos > have:          # the cursor was advanced past what has been generated
+                self._rs.random_sample(self.pos - have)
+                self._buf, self._base, have = np.zeros(0), self.pos, self.pos
             grow = max(end - have, 1 << 20)
             self._buf = np.concatenate([self._buf[self.pos - self._base:], self._rs.random_sample(grow)])
             self._base = self.pos

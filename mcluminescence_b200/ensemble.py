@@ -1,0 +1,107 @@
+"""Replica ensembles across GPUs: shard, run, one NCCL all-reduce of the integer histograms.
+
+Replicas never interact (``src/class/simulate.py:36,46``: independent loops), so ranks take
+contiguous blocks of global replica ids and run them with no data-path collective.  The only
+exchange is the final ensemble sum: every rank's fused integer histograms (events, occupancy,
+occupancy squared -- a few KB) are all-reduced once, plus a handful of scalar counters.
+Because the Philox streams are keyed by (seed, global replica id) and the histograms are
+integers, the result is identical for any number of ranks.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+from . import engine
+from .engine import HistSpec
+from .replicas import MODE_PHILOX
+
+
+def shard_bounds(n_total: int, world: int, rank: int):
+    """Contiguous block [lo, hi) of global replica ids owned by ``rank`` (sizes differ by <= 1)."""
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+@dataclass
+class EnsembleResult:
+    hist_events: np.ndarray      # [rows, bins] int64, summed over all replicas of all ranks
+    hist_occ: np.ndarray         # [rows, bins] int64  sum of n_e at each bin's left edge
+    hist_occ_sq: np.ndarray      # [rows, bins] int64  sum of n_e^2
+    n_replicas: int              # global
+    esteps: int                  # global electron-steps
+    steps: int                   # global steps
+    errors: int                  # replicas that ended with a non-zero status
+    final_n_e_sum: int
+
+    def mean_occupancy(self, replicas_per_row):
+        return self.hist_occ / np.asarray(replicas_per_row, dtype=np.float64)[:, None]
+
+    def std_occupancy(self, replicas_per_row):
+        n = np.asarray(replicas_per_row, dtype=np.float64)[:, None]
+        m = self.hist_occ / n
+        return np.sqrt(np.maximum(self.hist_occ_sq / n - m * m, 0.0))
+
+
+def run_ensemble(workload: Dict[str, Any], *, seed: int, rank: int = 0, world: int = 1,
+                 group=None, replica_id0: int = 0, shard: bool = True, device=None,
+                 reduce: bool = True):
+    """Run a workload dict (see ``workloads``) on this rank's shard and reduce across ranks.
+
+    ``shard=True``: the workload's replicas are the GLOBAL ensemble and this rank runs its block.
+    ``shard=False``: the replicas given are this rank's own (weak scaling); global ids are
+    ``replica_id0 + rank * len(replicas) + r``.
+    Returns ``(EnsembleResult, device_tensors)``; the tensors stay on the GPU for callers that time
+    the kernel separately from the read-back.
+    """
+    torch = engine._torch()
+    reps, segs = workload["replicas"], workload["segments"]
+    hist: Optional[HistSpec] = workload.get("hist")
+    grp = workload.get("hist_group")
+    if shard:
+        lo, hi = shard_bounds(len(reps), world, rank)
+        my = reps[lo:hi]
+        my_grp = grp[lo:hi] if grp is not None else None
+        id0 = replica_id0 + lo
+        n_global = len(reps)
+    else:
+        my, my_grp = reps, grp
+        id0 = replica_id0 + rank * len(reps)
+        n_global = len(reps) * world
+    out = engine.run_replicas(my, segs, workload["max_steps"], mode=MODE_PHILOX, seed=seed,
+                              replica_id0=id0, trace=False, hist=hist, hist_group=my_grp,
+                              device=device)
+    T = out.tensors
+    counters = torch.stack([T["esteps"].sum(), T["steps_used"].sum().to(torch.int64),
+                            (T["status"] != 0).sum().to(torch.int64), T["final_n_e"].sum().to(torch.int64)])
+    if reduce and world > 1:
+        import torch.distributed as dist
+        if hist is not None:
+            packed = torch.cat([T["hist_events"].reshape(-1), T["hist_occ"].reshape(-1),
+                                T["hist_occ_sq"].reshape(-1), counters])
+        else:
+            packed = counters
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        if hist is not None:
+            n = hist.n_groups * hist.n_bins
+            T["hist_events"] = packed[0:n].reshape(hist.n_groups, hist.n_bins)
+            T["hist_occ"] = packed[n:2 * n].reshape(hist.n_groups, hist.n_bins)
+            T["hist_occ_sq"] = packed[2 * n:3 * n].reshape(hist.n_groups, hist.n_bins)
+            counters = packed[3 * n:]
+        else:
+            counters = packed
+    T["counters"] = counters
+
+    def finish() -> EnsembleResult:
+        c = counters.cpu().numpy()
+        z = np.zeros((1, 1), np.int64)
+        return EnsembleResult(
+            hist_events=T["hist_events"].cpu().numpy() if hist is not None else z,
+            hist_occ=T["hist_occ"].cpu().numpy() if hist is not None else z,
+            hist_occ_sq=T["hist_occ_sq"].cpu().numpy() if hist is not None else z,
+            n_replicas=n_global, esteps=int(c[0]), steps=int(c[1]), errors=int(c[2]), final_n_e_sum=int(c[3]))
+
+    return finish, T

@@ -36,7 +36,7 @@ def ensemble_tables(overrides, R):
     return reps, segs, int(runs[0]["exp_type_fp"]["steps"])
 
 
-def stats(event, n_e, t, used, grid):
+def stats(event, n_e, t, used, grid, n_e0):
     """per-replica: events, final n_e, n_e sampled on a time grid; pooled event times."""
     R = event.shape[0]
     n_ev = np.array([event[r, :used[r]].sum() for r in range(R)], dtype=np.float64)
@@ -46,7 +46,7 @@ def stats(event, n_e, t, used, grid):
     for r in range(R):
         tt, ne = t[r, :used[r]], n_e[r, :used[r]]
         idx = np.searchsorted(tt, grid, side="right") - 1        # last step at or before the grid time
-        occ[r] = np.where(idx >= 0, ne[np.maximum(idx, 0)], np.nan)
+        occ[r] = np.where(idx >= 0, ne[np.maximum(idx, 0)], n_e0)
         times.append(tt[event[r, :used[r]] > 0])
     return n_ev, fin, occ, np.concatenate(times)
 
@@ -82,8 +82,8 @@ def test_simulate_ensemble_matches_oracle(gpu, name):
     out.raise_on_error()
     ref = mo.run(reps, segs, steps, seed=77, parallel=True)
     assert ref.rc == 0
-    g = stats(out.event, out.n_e, out.t, out.steps_used, grid)
-    o = stats(ref.event, ref.n_e, ref.t, ref.steps_used, grid)
+    g = stats(out.event, out.n_e, out.t, out.steps_used, grid, int(reps['n_e0'][0]))
+    o = stats(ref.event, ref.n_e, ref.t, ref.steps_used, grid, int(reps['n_e0'][0]))
     assert_means_agree(g[0], o[0], f"{name}: events per replica")
     assert_means_agree(g[1], o[1], f"{name}: final n_e")
     for k in range(len(grid)):
