@@ -23,6 +23,8 @@
 // in shared memory; coordinates (pre-scaled by alpha*log2 e) in the replica's HBM slab and only
 // touched on events.  Holes: [0,n_h0) sorted by grid cell (+cell_start table), [n_h0, ...) fills.
 #include <math_constants.h>
+#include <type_traits>
+#include <cstdlib>
 #include "mcl_common.cuh"
 
 namespace mcl {
@@ -43,6 +45,8 @@ struct Cfg {
     int cap_slots;     // even; smem slots per replica
     int g_max;         // largest grid edge the slab has room for
     int cap_cells;     // g_max^3 + 1
+    int bm_words;      // smem words of the initial-hole alive bitmap
+    size_t off_cand;   // byte offset of the candidate lists inside the slab
 };
 
 __device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
@@ -133,16 +137,93 @@ __device__ unsigned long long warp_nearest(const Holes &H, float x, float y, flo
     return warp_min_u64(best);
 }
 
+constexpr int KC = 4;      // candidate holes remembered per electron
+
+// Warp-cooperative search for the KC nearest alive holes of (x,y,z) among the INITIAL holes (the
+// grid region).  out[k] (sorted, all lanes) = bits(d2) << 32 | slot, ~0 when fewer exist.
+// While no hole is ever added (no fills), the nearest alive hole of an electron at any later time
+// is the first still-alive entry of this list, so a re-search after a recombination is a lookup.
+__device__ void warp_nearest_k(const Holes &H, float x, float y, float z, int lane, unsigned long long out[KC])
+{
+    const int G = H.G;
+    int cx = min(G - 1, max(0, (int)(x * H.inv_w)));
+    int cy = min(G - 1, max(0, (int)(y * H.inv_w)));
+    int cz = min(G - 1, max(0, (int)(z * H.inv_w)));
+    unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull, k3 = ~0ull;     // this lane's sorted best four
+    for (int R = 1;; R++) {
+        const int side = 2 * R + 1, ncb = side * side * side;
+        for (int idx = lane; idx < ncb; idx += 32) {
+            int oz = idx % side - R, oy = (idx / side) % side - R, ox = idx / (side * side) - R;
+            if (R > 1 && max(abs(ox), max(abs(oy), abs(oz))) < R) continue;
+            int ax = cx + ox, ay = cy + oy, az = cz + oz;
+            if ((unsigned)ax >= (unsigned)G || (unsigned)ay >= (unsigned)G || (unsigned)az >= (unsigned)G) continue;
+            int c = (ax * G + ay) * G + az;
+            int j0 = H.cell_start[c], j1 = H.cell_start[c + 1];
+            for (int j = j0; j < j1; j++) {
+                float dx = x - H.x[j], dy = y - H.y[j], dz = z - H.z[j];
+                float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
+                if (key < k3) {
+                    k3 = key;
+                    if (k3 < k2) { unsigned long long t = k2; k2 = k3; k3 = t; }
+                    if (k2 < k1) { unsigned long long t = k1; k1 = k2; k2 = t; }
+                    if (k1 < k0) { unsigned long long t = k0; k0 = k1; k1 = t; }
+                }
+            }
+        }
+        // merge the per-lane lists: KC rounds of "global minimum, its owner pops"
+        unsigned long long a0 = k0, a1 = k1, a2 = k2, a3 = k3;
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+            unsigned long long m = warp_min_u64(a0);
+            out[k] = m;
+            if (a0 == m && m != ~0ull) { a0 = a1; a1 = a2; a2 = a3; a3 = ~0ull; }
+        }
+        float bound = F_INF;
+        bool covered = true;
+        if (cx - R > 0) { bound = fminf(bound, x - (cx - R) * H.w); covered = false; }
+        if (cx + R < G - 1) { bound = fminf(bound, (cx + R + 1) * H.w - x); covered = false; }
+        if (cy - R > 0) { bound = fminf(bound, y - (cy - R) * H.w); covered = false; }
+        if (cy + R < G - 1) { bound = fminf(bound, (cy + R + 1) * H.w - y); covered = false; }
+        if (cz - R > 0) { bound = fminf(bound, z - (cz - R) * H.w); covered = false; }
+        if (cz + R < G - 1) { bound = fminf(bound, (cz + R + 1) * H.w - z); covered = false; }
+        float d2k = __uint_as_float((uint32_t)(out[KC - 1] >> 32));     // NaN bits when the list is short
+        if (covered || d2k <= bound * bound) break;
+    }
+}
+
 template <int NT>
 __device__ __forceinline__ void cta_sync()
 {
     if (NT > 32) __syncthreads(); else __syncwarp();
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const RoundKeys K, const Cfg cfg)
+// NearT: type of the per-electron nearest-hole slot kept in shared memory.  uint16_t whenever the
+// hole capacity allows (halves the footprint and the traffic of the post-event scan); the all-ones
+// value marks an empty electron slot.
+template <typename NearT> struct NearTraits;
+template <> struct NearTraits<uint16_t> { static constexpr uint32_t DEAD = 0xffffu; static constexpr int PER_VEC = 8; };
+template <> struct NearTraits<uint32_t> { static constexpr uint32_t DEAD = 0xffffffffu; static constexpr int PER_VEC = 4; };
+
+// candidate test of one 16-byte vector of slots against hole h (and h2): may report false
+// positives (borrow of the zero-halfword trick), never false negatives; the slow path re-checks.
+__device__ __forceinline__ bool vec_may_match(const uint4 w, uint32_t h, uint16_t)
+{
+    const uint32_t hh = h * 0x00010001u;
+    auto zh = [](uint32_t t) { return (t - 0x00010001u) & ~t & 0x80008000u; };
+    return (zh(w.x ^ hh) | zh(w.y ^ hh) | zh(w.z ^ hh) | zh(w.w ^ hh)) != 0u;
+}
+__device__ __forceinline__ bool vec_may_match(const uint4 w, uint32_t h, uint32_t)
+{
+    return (w.x == h) | (w.y == h) | (w.z == h) | (w.w == h);
+}
+
+template <int NT, int MINB, typename NearT>
+__global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, const RoundKeys K, const Cfg cfg)
 {
     constexpr int NW = NT / 32;
+    constexpr uint32_t NEAR_DEAD = NearTraits<NearT>::DEAD;
+    constexpr int PER_VEC = NearTraits<NearT>::PER_VEC;
     const int r = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const mcl_replica rp = p.replicas[r];
@@ -152,9 +233,11 @@ __global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const 
     // ---------------- shared memory
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *cr = reinterpret_cast<float *>(smem_raw);                  // [cap_slots]
-    int *near = reinterpret_cast<int *>(cr + cfg.cap_slots);          // [cap_slots]
+    NearT *near = reinterpret_cast<NearT *>(cr + cfg.cap_slots);      // [cap_slots]
+    uint32_t *hole_bm = reinterpret_cast<uint32_t *>(near + cfg.cap_slots);   // [bm_words] 1 = initial hole alive
     __shared__ float red_v[2][32];
     __shared__ int red_s[2][32];
+    __shared__ int red_h[2][32];
     __shared__ uint32_t stepdraw[2][4];
     __shared__ int rec_ev[32], rec_ne[32];
     __shared__ double rec_t[32];
@@ -169,6 +252,8 @@ __global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const 
     int *cell_start = hid + ch;                                       // [cap_cells]
     int *cell_fill = cell_start + cfg.cap_cells;                      // [cap_cells] init only
     int *flist = cell_fill + cfg.cap_cells;                           // [cap_e]
+    float4 *cand_d = reinterpret_cast<float4 *>(ws + cfg.off_cand);   // [cap_e] cr of the KC nearest initial holes
+    NearT *cand_j = reinterpret_cast<NearT *>(cand_d + ce);           // [cap_e][KC] their slots (NEAR_DEAD = none)
 
     int status = MCL_OK;
     const float core_s = (float)(rp.side * rp.alpha * L2E);
@@ -184,7 +269,8 @@ __global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const 
     H.w = bnd_s / (float)H.G; H.inv_w = (float)H.G / bnd_s;
     const int n_cells = H.G * H.G * H.G;
 
-    for (int s = tid; s < cfg.cap_slots; s += NT) { cr[s] = F_INF; near[s] = -1; }
+    for (int s = tid; s < cfg.cap_slots; s += NT) { cr[s] = F_INF; near[s] = (NearT)NEAR_DEAD; }
+    for (int w = tid; w < cfg.bm_words; w += NT) hole_bm[w] = 0xffffffffu;
     if (tid == 0) s_nflag = 0;
 
     if (status == MCL_OK) {
@@ -247,8 +333,19 @@ __global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const 
         cta_sync<NT>();
         // Box._rebuild (engine.py:113-119): nearest hole of every electron, one warp per electron
         for (int i = warp; i < n_e; i += NW) {
-            unsigned long long b = warp_nearest(H, ex[i], ey[i], ez[i], lane);
-            if (lane == 0) { cr[i] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[i] = (int)(uint32_t)b; }
+            unsigned long long b[KC];
+            warp_nearest_k(H, ex[i], ey[i], ez[i], lane, b);
+            if (lane == 0) {
+                float d[KC];
+#pragma unroll
+                for (int k = 0; k < KC; k++) {
+                    const bool ok = b[k] != ~0ull;
+                    d[k] = ok ? sqrtf(__uint_as_float((uint32_t)(b[k] >> 32))) : F_INF;
+                    cand_j[(size_t)i * KC + k] = ok ? (NearT)(uint32_t)b[k] : (NearT)NEAR_DEAD;
+                }
+                cand_d[i] = make_float4(d[0], d[1], d[2], d[3]);
+                cr[i] = d[0]; near[i] = b[0] != ~0ull ? (NearT)(uint32_t)b[0] : (NearT)NEAR_DEAD;
+            }
         }
         cta_sync<NT>();
     }
@@ -347,36 +444,40 @@ __global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const 
             float best = F_INF; int bslot = -1;
             const int n_pairs = (n_slots + 1) >> 1;
             const float2 *cr2 = reinterpret_cast<const float2 *>(cr);
-            for (int q = tid; q < n_pairs; q += NT) {
-                const float2 c = cr2[q];
-                uint32_t c0 = (uint32_t)q, c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);
-                philox4x32_10(c0, c1, c2, c3, K);
-                float a0 = ((c0 < thr) ? A2 : A1) - c.x;
-                float a1 = ((c2 < thr) ? A2 : A1) - c.y;
-                float le0 = lg2_fast(-lg2_fast(u01(c1)));
-                float le1 = lg2_fast(-lg2_fast(u01(c3)));
-                float l0, l1;
-                if (has_cb) {
-                    // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
-                    float m0 = fmaxf(a0, g), m1 = fmaxf(a1, g);
-                    float k0 = m0 + lg2_fast(1.0f + ex2_fast(-fabsf(a0 - g)));
-                    float k1 = m1 + lg2_fast(1.0f + ex2_fast(-fabsf(a1 - g)));
-                    l0 = (le0 - k0) + (c.x - c.x);
-                    l1 = (le1 - k1) + (c.y - c.y);
-                } else {
-                    l0 = le0 - a0;
-                    l1 = le1 - a1;
+            auto pair_loop = [&](auto with_cb) {
+                constexpr bool CB = decltype(with_cb)::value;
+                for (int q = tid; q < n_pairs; q += NT) {
+                    const float2 c = cr2[q];
+                    uint32_t c0 = (uint32_t)q, c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);
+                    philox4x32_10(c0, c1, c2, c3, K);
+                    float a0 = ((c0 < thr) ? A2 : A1) - c.x;
+                    float a1 = ((c2 < thr) ? A2 : A1) - c.y;
+                    float le0 = lg2_fast(-lg2_fast(u01(c1)));
+                    float le1 = lg2_fast(-lg2_fast(u01(c3)));
+                    float l0, l1;
+                    if (CB) {
+                        // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
+                        float m0 = fmaxf(a0, g), m1 = fmaxf(a1, g);
+                        float k0 = m0 + lg2_fast(1.0f + ex2_fast(-fabsf(a0 - g)));
+                        float k1 = m1 + lg2_fast(1.0f + ex2_fast(-fabsf(a1 - g)));
+                        l0 = (le0 - k0) + (c.x - c.x);
+                        l1 = (le1 - k1) + (c.y - c.y);
+                    } else {
+                        l0 = le0 - a0;
+                        l1 = le1 - a1;
+                    }
+                    if (l0 < best) { best = l0; bslot = 2 * q; }
+                    if (l1 < best) { best = l1; bslot = 2 * q + 1; }
                 }
-                if (l0 < best) { best = l0; bslot = 2 * q; }
-                if (l1 < best) { best = l1; bslot = 2 * q + 1; }
-            }
+            };
+            if (has_cb) pair_loop(std::true_type{}); else pair_loop(std::false_type{});
             // warp argmin -> one row per warp
             {
                 float wv = warp_min_f32(best);
                 unsigned m = __ballot_sync(0xffffffffu, best == wv);
                 int src = m ? (__ffs(m) - 1) : 0;
                 int ws_ = __shfl_sync(0xffffffffu, bslot, src);
-                if (lane == 0) { red_v[par][warp] = wv; red_s[par][warp] = ws_; }
+                if (lane == 0) { red_v[par][warp] = wv; red_s[par][warp] = ws_; red_h[par][warp] = ws_ >= 0 ? (int)near[ws_] : -1; }
             }
             if (warp == 0) {
                 // step scalars: fill clock + coordinates of a would-be new electron / hole
@@ -387,13 +488,16 @@ __global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const 
                 }
             }
             cta_sync<NT>();                                   // ===== B1
-            float vmin; int smin;
+            float vmin; int smin, hmin;
             {
                 float v = lane < NW ? red_v[par][lane] : F_INF;
                 int s = lane < NW ? red_s[par][lane] : -1;
+                int hh = lane < NW ? red_h[par][lane] : -1;
                 vmin = warp_min_f32(v);
                 unsigned m = __ballot_sync(0xffffffffu, v == vmin);
-                smin = __shfl_sync(0xffffffffu, s, m ? (__ffs(m) - 1) : 0);
+                const int src = m ? (__ffs(m) - 1) : 0;
+                smin = __shfl_sync(0xffffffffu, s, src);
+                hmin = __shfl_sync(0xffffffffu, hh, src);
             }
             // ---------------- filling clock (tl_trap_lab.py:53-60) and dt (simulate.py:58-60)
             float dt_fill;
@@ -434,8 +538,8 @@ __global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const 
             if (is_rec) {
                 // ---------------- Box.remove_pair (engine.py:154-175)
                 ev = 1;
-                const int h = near[smin];
-                if (tid == ((smin >> 1) % NT)) cr[smin] = F_INF;       // owner of the pair tombstones it
+                const int h = hmin;                                    // nearest hole of the winner (read before B1)
+                if (tid == ((smin >> 1) % NT)) { cr[smin] = F_INF; near[smin] = (NearT)NEAR_DEAD; }   // owner tombstones it
                 n_e--;
                 int h2 = -1;
                 if (ever_filled) {
@@ -445,20 +549,46 @@ __global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const 
                 }
                 if (tid == 0) {
                     hx[h] = DEAD_X;
-                    if (h >= n_h0) { /* fill-region hole */ }
+                    if (h < n_h0) hole_bm[h >> 5] &= ~(1u << (h & 31));
                     if (hist_on && p.hist_events) {
                         int b = bin_of(t_cur);
                         if (b >= 0) atomicAdd(&p.hist_events[(size_t)hrow * p.hist.n_bins + b], 1ull);
                     }
                 }
                 if (h >= n_h0) n_fill_alive--;
+                // which other electrons were cached on h (or h2)?  16 bytes of slots per load
                 bool mine = false;
-                const int2 *near2 = reinterpret_cast<const int2 *>(near);
-                for (int q = tid; q < n_pairs; q += NT) {
-                    const int2 nn = near2[q];
-                    const float2 c = cr2[q];
-                    if ((nn.x == h || nn.x == h2) && c.x < F_INF) { flist[atomicAdd(&s_nflag, 1)] = 2 * q; mine = true; }
-                    if ((nn.y == h || nn.y == h2) && c.y < F_INF) { flist[atomicAdd(&s_nflag, 1)] = 2 * q + 1; mine = true; }
+                {
+                    const uint4 *nv = reinterpret_cast<const uint4 *>(near);
+                    const int n_vec = (n_slots + PER_VEC - 1) / PER_VEC;
+                    for (int v = tid; v < n_vec; v += NT) {
+                        const uint4 w = nv[v];
+                        bool hit = vec_may_match(w, (uint32_t)h, NearT());
+                        if (h2 >= 0) hit |= vec_may_match(w, (uint32_t)h2, NearT());
+                        if (hit) {
+                            for (int k = 0; k < PER_VEC; k++) {
+                                const int sl = v * PER_VEC + k;
+                                const uint32_t nn = near[sl];
+                                if (sl != smin && (nn == (uint32_t)h || (h2 >= 0 && nn == (uint32_t)h2))) {
+                                    bool fixed = false;
+                                    if (!ever_filled) {
+                                        // no hole was ever added: the new nearest is the first remembered
+                                        // candidate that is still alive (and is not the hole dying now)
+                                        const float4 d4 = cand_d[sl];
+                                        const float dk[KC] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                                        for (int c = 0; c < KC; c++) {
+                                            const uint32_t j = cand_j[(size_t)sl * KC + c];
+                                            if (!fixed && j != NEAR_DEAD && j != (uint32_t)h && ((hole_bm[j >> 5] >> (j & 31)) & 1u)) {
+                                                cr[sl] = dk[c]; near[sl] = (NearT)j; fixed = true;
+                                            }
+                                        }
+                                    }
+                                    if (!fixed) { flist[atomicAdd(&s_nflag, 1)] = sl; mine = true; }
+                                }
+                            }
+                        }
+                    }
                 }
                 int any_flag;
                 if (NT > 32) any_flag = __syncthreads_or(mine);       // ===== B2
@@ -468,7 +598,7 @@ __global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const 
                     for (int f = warp; f < nflag; f += NW) {
                         int s = flist[f];
                         unsigned long long b = warp_nearest(H, ex[s], ey[s], ez[s], lane);
-                        if (lane == 0) { cr[s] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[s] = (int)(uint32_t)b; }
+                        if (lane == 0) { cr[s] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[s] = (NearT)(uint32_t)b; }
                     }
                     cta_sync<NT>();                           // ===== B3
                     if (tid == 0) s_nflag = 0;
@@ -480,10 +610,21 @@ __global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const 
                     for (int base = 0; base < n_slots; base += NT) {
                         int s = base + tid;
                         float c = s < n_slots ? cr[s] : F_INF;
-                        int nn = s < n_slots ? near[s] : -1;
+                        NearT nn = s < n_slots ? near[s] : (NearT)NEAR_DEAD;
                         bool alive = c < F_INF;
                         float x = 0.f, y = 0.f, z = 0.f;
-                        if (alive) { x = ex[s]; y = ey[s]; z = ez[s]; }
+                        float4 cd = make_float4(0.f, 0.f, 0.f, 0.f);
+                        NearT cj[KC];
+#pragma unroll
+                        for (int k = 0; k < KC; k++) cj[k] = (NearT)NEAR_DEAD;
+                        if (alive) {
+                            x = ex[s]; y = ey[s]; z = ez[s];
+                            if (!ever_filled) {
+                                cd = cand_d[s];
+#pragma unroll
+                                for (int k = 0; k < KC; k++) cj[k] = cand_j[(size_t)s * KC + k];
+                            }
+                        }
                         unsigned m = __ballot_sync(0xffffffffu, alive);
                         int wpre = __popc(m & ((1u << lane) - 1u));
                         if (lane == 0) s_scan[warp] = __popc(m);
@@ -493,11 +634,18 @@ __global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const 
                         for (int k = 0; k < NW; k++) { int v = s_scan[k]; if (k < warp) woff += v; tot += v; }
                         int dst = run + woff + wpre;
                         cta_sync<NT>();                       // all reads of this tile done
-                        if (alive) { cr[dst] = c; near[dst] = nn; ex[dst] = x; ey[dst] = y; ez[dst] = z; }
+                        if (alive) {
+                            cr[dst] = c; near[dst] = nn; ex[dst] = x; ey[dst] = y; ez[dst] = z;
+                            if (!ever_filled) {
+                                cand_d[dst] = cd;
+#pragma unroll
+                                for (int k = 0; k < KC; k++) cand_j[(size_t)dst * KC + k] = cj[k];
+                            }
+                        }
                         run += tot;
                     }
                     cta_sync<NT>();
-                    for (int s = run + tid; s < n_slots; s += NT) { cr[s] = F_INF; near[s] = -1; }
+                    for (int s = run + tid; s < n_slots; s += NT) { cr[s] = F_INF; near[s] = (NearT)NEAR_DEAD; }
                     n_slots = run;
                     cta_sync<NT>();
                 }
@@ -535,7 +683,7 @@ __global__ void __launch_bounds__(NT) philox_kernel(const LaunchParams p, const 
                     unsigned long long b = warp_nearest(H, nx, ny, nz, lane);     // OLD holes only
                     if (lane == 0) {
                         ex[es] = nx; ey[es] = ny; ez[es] = nz;
-                        cr[es] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[es] = (int)(uint32_t)b;
+                        cr[es] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[es] = (NearT)(uint32_t)b;
                         hx[hs] = qx; hy[hs] = qy; hz[hs] = qz;
                     }
                 }
@@ -591,61 +739,72 @@ static int grid_edge_max(int n_h0_max)
     return g < 1 ? 1 : g;
 }
 
-struct PhiloxPlan { int nt; int cap_slots; int g_max; int cap_cells; size_t smem; };
+struct PhiloxPlan { int nt; int cap_slots; int g_max; int cap_cells; int bm_words; size_t smem; size_t off_cand; size_t stride; bool near16; };
 
-static PhiloxPlan make_plan(int cap_e, int n_h0_max, int nt_override)
+static int g_nt_override = 0;
+void philox_set_block_threads(int nt) { g_nt_override = nt; }
+
+static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override)
 {
     PhiloxPlan pl;
     pl.cap_slots = (int)align_up((size_t)cap_e + 2, 64);
-    pl.g_max = grid_edge_max(n_h0_max);
+    pl.g_max = grid_edge_max(cap_h);          // n_h0 <= cap_h: always enough room for the cell tables
     pl.cap_cells = pl.g_max * pl.g_max * pl.g_max + 1;
-    pl.smem = (size_t)pl.cap_slots * 8;
+    pl.near16 = cap_h <= 65534;
+    pl.bm_words = (cap_h + 31) / 32;
+    pl.smem = (size_t)pl.cap_slots * (4 + (pl.near16 ? 2 : 4)) + 4 * (size_t)pl.bm_words;
+    size_t b = sizeof(float) * 3 * ((size_t)cap_e + (size_t)cap_h) + sizeof(int) * ((size_t)cap_h + 2 * (size_t)pl.cap_cells + (size_t)cap_e);
+    pl.off_cand = align_up(b, 16);
+    pl.stride = align_up(pl.off_cand + (size_t)cap_e * (16 + 4 * (pl.near16 ? 2 : 4)), 256);
     int nt;
     if (cap_e <= 256) nt = 32;
     else if (cap_e <= 1024) nt = 64;
     else if (cap_e <= 4096) nt = 128;
     else nt = 256;
+    if (const char *env = getenv("MCL_PHILOX_NT")) nt_override = atoi(env);     // tuning knob
     if (nt_override == 32 || nt_override == 64 || nt_override == 128 || nt_override == 256 || nt_override == 512)
         nt = nt_override;
     pl.nt = nt;
     return pl;
 }
 
-static int g_nt_override = 0;
-void philox_set_block_threads(int nt) { g_nt_override = nt; }
-
 size_t philox_ws_stride(int cap_e, int cap_h)
 {
-    // n_h0_max <= cap_h, so sizing the cell tables from cap_h is always enough
-    PhiloxPlan pl = make_plan(cap_e, cap_h, 0);
-    size_t b = sizeof(float) * 3 * ((size_t)cap_e + (size_t)cap_h) + sizeof(int) * ((size_t)cap_h + 2 * (size_t)pl.cap_cells + (size_t)cap_e);
-    return align_up(b, 256);
+    return make_plan(cap_e, cap_h, 0).stride;
+}
+
+template <int NT, int MINB, typename NearT>
+static cudaError_t launch_one(const LaunchParams &p, const RoundKeys &K, const Cfg &cfg, size_t smem, cudaStream_t stream)
+{
+    cudaError_t e = cudaFuncSetAttribute(philox_kernel<NT, MINB, NearT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    philox_kernel<NT, MINB, NearT><<<p.n_replicas, NT, smem, stream>>>(p, K, cfg);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_slots*/)
 {
     PhiloxPlan pl = make_plan(p.cap_e, p.cap_h, g_nt_override);
-    Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells};
+    Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.off_cand};
     RoundKeys K;
     uint64_t s = mix64(p.seed);
     uint32_t k0 = (uint32_t)s, k1 = (uint32_t)(s >> 32);
     for (int r = 0; r < 10; r++) { K.k[2 * r] = k0; K.k[2 * r + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
-    cudaError_t e = cudaSuccess;
-#define MCL_LAUNCH(NT_)                                                                                   \
-    do {                                                                                                  \
-        e = cudaFuncSetAttribute(philox_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem); \
-        if (e != cudaSuccess) return e;                                                                   \
-        philox_kernel<NT_><<<p.n_replicas, NT_, pl.smem, stream>>>(p, K, cfg);                            \
-    } while (0)
+    // MINB caps the register count at 64 per thread (32 resident warps per SM when smem allows)
+#define MCL_CASE(NT_, MINB_)                                                                       \
+    case NT_:                                                                                      \
+        return pl.near16 ? launch_one<NT_, MINB_, uint16_t>(p, K, cfg, pl.smem, stream)            \
+                         : launch_one<NT_, MINB_, uint32_t>(p, K, cfg, pl.smem, stream)
     switch (pl.nt) {
-        case 32: MCL_LAUNCH(32); break;
-        case 64: MCL_LAUNCH(64); break;
-        case 128: MCL_LAUNCH(128); break;
-        case 256: MCL_LAUNCH(256); break;
-        default: MCL_LAUNCH(512); break;
+        MCL_CASE(32, 32);
+        MCL_CASE(64, 16);
+        MCL_CASE(128, 8);
+        MCL_CASE(256, 3);
+        default: break;
     }
-#undef MCL_LAUNCH
-    return cudaGetLastError();
+    return pl.near16 ? launch_one<512, 2, uint16_t>(p, K, cfg, pl.smem, stream)
+                     : launch_one<512, 2, uint32_t>(p, K, cfg, pl.smem, stream);
+#undef MCL_CASE
 }
 
 }  // namespace mcl
