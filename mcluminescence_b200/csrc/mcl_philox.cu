@@ -400,23 +400,26 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         const int hrow = hist_on ? (hgroup * rp.seg_count + sg) : 0;
         int hbin_next = 0;        // next bin whose left edge has not been passed yet
 
-        auto edge = [&](int k) -> double {          // left edge of bin k on the leg's axis, as a time
-            double f = (double)k / (double)p.hist.n_bins;
-            if (p.hist.axis == MCL_AXIS_TIME_LIN) return p.hist.lo + f * (p.hist.hi - p.hist.lo);
-            if (p.hist.axis == MCL_AXIS_TIME_LOG) return exp10(log10(p.hist.lo) + f * (log10(p.hist.hi) - log10(p.hist.lo)));
-            double Tedge = p.hist.lo + f * (p.hist.hi - p.hist.lo);      // deg C
-            return S.T_rate > 0.0 ? (Tedge - S.T_start) / S.T_rate : CUDART_INF;
+        // Histogram axis of this leg.  Bin edges are visited in order, so the cursor (hbin_next, hedge_next)
+        // also tells which bin an event falls in: no per-event logarithm.  On the log-time axis the next edge
+        // is the previous one times a constant ratio.
+        const bool h_log = hist_on && p.hist.axis == MCL_AXIS_TIME_LOG;
+        const bool h_temp = hist_on && p.hist.axis == MCL_AXIS_TEMP;
+        const bool h_mono = hist_on && (!h_temp || S.T_rate > 0.0);       // cooling legs: events only, via bin_of
+        const double h_ratio = h_log ? exp10((log10(p.hist.hi) - log10(p.hist.lo)) / (double)p.hist.n_bins) : 1.0;
+        const double h_step = (p.hist.hi - p.hist.lo) / (double)(hist_on ? p.hist.n_bins : 1);
+        auto edge_after = [&](int k, double prev) -> double {   // left edge of bin k, given the edge of bin k-1
+            if (h_log) return prev * h_ratio;
+            const double v = p.hist.lo + (double)k * h_step;
+            return h_temp ? (v - S.T_start) / S.T_rate : v;
         };
-        auto bin_of = [&](double t) -> int {
-            double f;
-            if (p.hist.axis == MCL_AXIS_TIME_LIN) f = (t - p.hist.lo) / (p.hist.hi - p.hist.lo);
-            else if (p.hist.axis == MCL_AXIS_TIME_LOG)
-                f = t > 0.0 ? (log10(t) - log10(p.hist.lo)) / (log10(p.hist.hi) - log10(p.hist.lo)) : -1.0;
-            else f = (S.T_start + S.T_rate * t - p.hist.lo) / (p.hist.hi - p.hist.lo);
+        auto bin_of = [&](double t) -> int {                    // only for non-monotonic (cooling) legs
+            const double f = (S.T_start + S.T_rate * t - p.hist.lo) / (p.hist.hi - p.hist.lo);
             if (!(f >= 0.0) || !(f < 1.0)) return -1;
             return min(p.hist.n_bins - 1, (int)(f * p.hist.n_bins));
         };
-        double hedge_next = hist_on ? edge(0) : CUDART_INF;
+        double hedge_next = CUDART_INF;
+        if (h_mono) hedge_next = h_log ? p.hist.lo : edge_after(0, 0.0);
 
         for (;;) {
             // ---------------- loop condition (simulate.py:51; tl_trap_lab.py:90,147)
@@ -521,15 +524,16 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             const double t_new = t_cur + (double)dt;
 
             // ---------------- fused occupancy histogram: edges passed while n_e was n_before
-            if (hist_on && p.hist_occ && hedge_next <= t_new) {
-                while (hbin_next < p.hist.n_bins && hedge_next <= t_new) {
-                    if (tid == 0) {
+            if (hedge_next <= t_new) {
+                // hbin_next <= n_bins; edge n_bins (the right end of the axis) closes the last bin
+                while (hedge_next <= t_new) {
+                    if (tid == 0 && p.hist_occ && hbin_next < p.hist.n_bins) {
                         size_t q = (size_t)hrow * p.hist.n_bins + hbin_next;
                         atomicAdd(&p.hist_occ[q], (unsigned long long)n_before);
                         if (p.hist_occ_sq) atomicAdd(&p.hist_occ_sq[q], (unsigned long long)n_before * (unsigned long long)n_before);
                     }
                     hbin_next++;
-                    hedge_next = hbin_next < p.hist.n_bins ? edge(hbin_next) : CUDART_INF;
+                    hedge_next = hbin_next <= p.hist.n_bins ? edge_after(hbin_next, hedge_next) : CUDART_INF;
                 }
             }
             t_cur = t_new;
@@ -551,8 +555,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     hx[h] = DEAD_X;
                     if (h < n_h0) hole_bm[h >> 5] &= ~(1u << (h & 31));
                     if (hist_on && p.hist_events) {
-                        int b = bin_of(t_cur);
-                        if (b >= 0) atomicAdd(&p.hist_events[(size_t)hrow * p.hist.n_bins + b], 1ull);
+                        // edges up to t_cur have been passed: the event sits in the bin before the cursor
+                        const int b = h_mono ? (hbin_next - 1) : bin_of(t_cur);
+                        if (b >= 0 && b < p.hist.n_bins) atomicAdd(&p.hist_events[(size_t)hrow * p.hist.n_bins + b], 1ull);
                     }
                 }
                 if (h >= n_h0) n_fill_alive--;
