@@ -261,9 +261,16 @@ def main():
             hbm_peak, hbm_src = float(mp["hbm_gbs"]), "measured"
         except Exception:  # noqa: BLE001
             hbm_peak, hbm_src = 6650.0, "fallback"
+        traffic = None
+        try:        # DRAM bytes of this kernel from the committed `ncu --set full` capture, scaled per replica
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_c2.json")))
+            if tr["workload"] == args.workload:
+                traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["replicas_in_capture"] * len(wl["replicas"])
+        except Exception:  # noqa: BLE001
+            pass
         roofline = {
             "bound": "sfu_fp32_issue", "achieved": achieved, "peak": peak_measured, "unit": UNIT,
-            "frac": achieved / peak_measured, "traffic": None,
+            "frac": achieved / peak_measured, "traffic": traffic,
             "kernel": "philox_kernel", "model": f"{SFU_PER_ESTEP:g} SFU + {LANEOPS_PER_ESTEP:g} FP32/INT32 lane-ops per electron-step",
             "peak_source": "mcl_device_peaks microbenchmarks in this run (MUFU, FFMA issue)",
             "peak_nominal": peak_nominal, "frac_nominal": achieved / peak_nominal,

@@ -449,6 +449,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             const float2 *cr2 = reinterpret_cast<const float2 *>(cr);
             auto pair_loop = [&](auto with_cb) {
                 constexpr bool CB = decltype(with_cb)::value;
+#pragma unroll (NT >= 256 ? 2 : 1)
                 for (int q = tid; q < n_pairs; q += NT) {
                     const float2 c = cr2[q];
                     uint32_t c0 = (uint32_t)q, c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);

@@ -26,6 +26,29 @@ def shard_bounds(n_total: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def allreduce_ensemble(T: Dict[str, Any], hist: Optional[HistSpec], counters, group=None):
+    """The ONE collective of the path: sum the integer histograms and the scalar counters over ranks.
+
+    Everything is packed into a single int64 vector so that exactly one all-reduce (NCCL on GPUs,
+    gloo in the CPU tests) is issued per ensemble.  Updates ``T`` in place, returns the counters.
+    """
+    import torch
+    import torch.distributed as dist
+    if hist is not None:
+        packed = torch.cat([T["hist_events"].reshape(-1), T["hist_occ"].reshape(-1),
+                            T["hist_occ_sq"].reshape(-1), counters])
+    else:
+        packed = counters.clone()
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    if hist is not None:
+        n = hist.n_groups * hist.n_bins
+        T["hist_events"] = packed[0:n].reshape(hist.n_groups, hist.n_bins)
+        T["hist_occ"] = packed[n:2 * n].reshape(hist.n_groups, hist.n_bins)
+        T["hist_occ_sq"] = packed[2 * n:3 * n].reshape(hist.n_groups, hist.n_bins)
+        return packed[3 * n:]
+    return packed
+
+
 @dataclass
 class EnsembleResult:
     hist_events: np.ndarray      # [rows, bins] int64, summed over all replicas of all ranks
@@ -78,21 +101,7 @@ def run_ensemble(workload: Dict[str, Any], *, seed: int, rank: int = 0, world: i
     counters = torch.stack([T["esteps"].sum(), T["steps_used"].sum().to(torch.int64),
                             (T["status"] != 0).sum().to(torch.int64), T["final_n_e"].sum().to(torch.int64)])
     if reduce and world > 1:
-        import torch.distributed as dist
-        if hist is not None:
-            packed = torch.cat([T["hist_events"].reshape(-1), T["hist_occ"].reshape(-1),
-                                T["hist_occ_sq"].reshape(-1), counters])
-        else:
-            packed = counters
-        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-        if hist is not None:
-            n = hist.n_groups * hist.n_bins
-            T["hist_events"] = packed[0:n].reshape(hist.n_groups, hist.n_bins)
-            T["hist_occ"] = packed[n:2 * n].reshape(hist.n_groups, hist.n_bins)
-            T["hist_occ_sq"] = packed[2 * n:3 * n].reshape(hist.n_groups, hist.n_bins)
-            counters = packed[3 * n:]
-        else:
-            counters = packed
+        counters = allreduce_ensemble(T, hist, counters, group)
     T["counters"] = counters
 
     def finish() -> EnsembleResult:

@@ -36,7 +36,7 @@ def lab_table(csv_name: str, protocol: int, root: Optional[str] = None) -> LabTa
 
 class TLTrapSim:
     def __init__(self, cfg: Mapping[str, Any], *, e_ratio_start: Optional[float] = None,
-                 rng: Optional[str] = None, seed: Optional[int] = None, device=None):
+                 rng: Optional[str] = None, seed: Optional[int] = None, candidate_id: int = 0, device=None):
         self.cfg = cfg
         self.mc = cfg["exp_type_fp"]
         self.phys = SimpleNamespace(**physics_record(cfg["physics_fp"]))   # TypeError like Physics(**...)
@@ -46,6 +46,7 @@ class TLTrapSim:
         self.rng = rng if rng is not None else str(cfg.get("rng", "philox"))
         self.seed = seed if seed is not None else cfg.get("seed", None)
         self.device = device
+        self.candidate_id = int(candidate_id)     # global id of this parameter set (Philox stream key)
         self.last_esteps = 0
         if self.rng == "replay":
             # the reference constructor seeds a Box: 3*(e0 + n_h0) uniforms leave the global stream
@@ -65,6 +66,7 @@ class TLTrapSim:
         else:
             seed = self.seed if self.seed is not None else int.from_bytes(os.urandom(8), "little")
             out = engine.run_replicas(reps, segs, steps, mode=MODE_PHILOX, seed=int(seed),
+                                      replica_id0=self.candidate_id * lt.n_rows,
                                       obs_time=lt.obs_time, trace=False, device=self.device)
             status = out.status
             final_n_e, obs_n_e, esteps = out.final_n_e, out.obs_n_e, out.esteps

@@ -1,0 +1,152 @@
+"""GPU: multi-leg schedules, the fused integer histograms, sharding invariance and the batched objective."""
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("marked gpu but no CUDA device is visible")
+    from mcluminescence_b200 import _native
+    _native.load()
+    return torch
+
+
+def two_leg_workload(R=96, n_e=200, n_bins=40):
+    from mcluminescence_b200 import workloads
+    from mcluminescence_b200.engine import AXIS_TIME_LOG, HistSpec
+    wl = workloads.c2(n_replicas=R, n_e=n_e, n_bins=n_bins)
+    wl["segments"]["duration"] = [200.0, 500.0]
+    wl["segments"]["A_opt"] = [0.0, 50.0]
+    wl["hist"] = HistSpec(axis=AXIS_TIME_LOG, n_bins=n_bins, lo=1e-2, hi=1e3, n_groups=2)
+    wl["max_steps"] = 4000
+    return wl
+
+
+def rebin(wl, event, n_e, t, used, n_e0):
+    """The kernel's histogram definition restated in NumPy from its own per-step trace."""
+    h = wl["hist"]
+    ratio = 10.0 ** ((np.log10(h.hi) - np.log10(h.lo)) / h.n_bins)
+    edges = [h.lo]
+    for _ in range(h.n_bins):
+        edges.append(edges[-1] * ratio)                # same recurrence as the kernel
+    edges = np.array(edges)
+    n_seg = len(wl["segments"])
+    ev = np.zeros((n_seg, h.n_bins), np.int64); occ = np.zeros_like(ev); occ2 = np.zeros_like(ev)
+    durs = wl["segments"]["duration"]
+    for r in range(event.shape[0]):
+        seg, t_off, cursor, n_prev = 0, 0.0, 0, n_e0
+        for i in range(used[r]):
+            t_loc = t[r, i] - t_off
+            while cursor <= h.n_bins and edges[cursor] <= t_loc:
+                if cursor < h.n_bins:
+                    occ[seg, cursor] += n_prev; occ2[seg, cursor] += n_prev * n_prev
+                cursor += 1
+            if event[r, i]:
+                b = cursor - 1
+                if 0 <= b < h.n_bins:
+                    ev[seg, b] += 1
+            n_prev = n_e[r, i]
+            if t_loc >= durs[seg] and seg + 1 < n_seg:      # the leg ends with the step that passes its duration
+                seg += 1; t_off = t[r, i]; cursor = 0
+    return ev, occ, occ2
+
+
+def test_fused_histograms_equal_rebinned_traces(gpu):
+    from mcluminescence_b200 import engine
+    wl = two_leg_workload()
+    out = engine.run_replicas(wl["replicas"], wl["segments"], wl["max_steps"], seed=11, hist=wl["hist"],
+                              trace=True, sync=True)
+    out.raise_on_error()
+    ev, occ, occ2 = rebin(wl, out.event, out.n_e, out.t, out.steps_used, int(wl["replicas"]["n_e0"][0]))
+    assert np.array_equal(out.hist_events, ev)
+    assert np.array_equal(out.hist_occ, occ)
+    assert np.array_equal(out.hist_occ_sq, occ2)
+    assert ev[0].sum() > 0 and ev[1].sum() > 0          # both legs produced luminescence
+    assert int(out.hist_events.sum()) <= int(out.event.sum())
+
+
+def test_two_leg_schedule_matches_oracle_statistically(gpu):
+    from mcluminescence_b200 import engine
+    from oracle import mcl_oracle as mo
+    wl = two_leg_workload(R=256)
+    out = engine.run_replicas(wl["replicas"], wl["segments"], wl["max_steps"], seed=5, sync=True)
+    out.raise_on_error()
+    ref = mo.run(wl["replicas"], wl["segments"], wl["max_steps"], seed=31, parallel=True)
+    assert ref.rc == 0
+    durs = wl["segments"]["duration"]
+
+    def per_leg(event, t, used):
+        a = np.zeros((event.shape[0], 2))
+        for r in range(event.shape[0]):
+            tt, e = t[r, :used[r]], event[r, :used[r]]
+            k = int(np.searchsorted(tt, durs[0], side="left")) + 1     # steps of leg 0 (incl. the overshooting one)
+            a[r] = e[:k].sum(), e[k:].sum()
+        return a
+
+    g, o = per_leg(out.event, out.t, out.steps_used), per_leg(ref.event, ref.t, ref.steps_used)
+    for leg in range(2):
+        se = np.sqrt(g[:, leg].var(ddof=1) / len(g) + o[:, leg].var(ddof=1) / len(o))
+        assert abs(g[:, leg].mean() - o[:, leg].mean()) <= 4 * se, (leg, g[:, leg].mean(), o[:, leg].mean())
+    se = np.sqrt(out.final_n_e.var(ddof=1) / len(g) + ref.final_n_e.var(ddof=1) / len(o))
+    assert abs(out.final_n_e.mean() - ref.final_n_e.mean()) <= 4 * se
+
+
+def test_ensemble_is_invariant_to_sharding(gpu):
+    """Integer histograms + (seed, global replica id) keyed streams: any split sums to the same result."""
+    from mcluminescence_b200 import ensemble
+    wl = two_leg_workload(R=60)
+    full, _ = ensemble.run_ensemble(wl, seed=3)
+    full = full()
+    parts = []
+    for rank in range(3):
+        fin, _ = ensemble.run_ensemble(wl, seed=3, rank=rank, world=3, reduce=False)
+        parts.append(fin())
+    assert np.array_equal(sum(p.hist_events for p in parts), full.hist_events)
+    assert np.array_equal(sum(p.hist_occ for p in parts), full.hist_occ)
+    assert np.array_equal(sum(p.hist_occ_sq for p in parts), full.hist_occ_sq)
+    assert sum(p.esteps for p in parts) == full.esteps and full.errors == 0
+
+
+def test_objective_batched_equals_single_candidate_calls(gpu, capsys):
+    from mcluminescence_b200 import optimizer
+    from mcluminescence_b200.config import compose
+    from mcluminescence_b200.workloads import c4_candidates
+    cfg = compose(overrides=helpers.LAB_OVERRIDES)
+    P = c4_candidates(8, seed=4)                       # [10, 8]
+    for exp in ("tl_clbr", "iso"):
+        batch = optimizer.objective_batched(P, cfg, exp, seed=21)
+        assert batch.shape == (8,) and np.all(np.isfinite(batch)) and np.all(batch >= 0)
+        for c in (0, 3, 7):
+            one = optimizer.objective(P[:, c], cfg, exp, seed=21, candidate_id=c)
+            assert one == batch[c], (exp, c)
+    with pytest.raises(ValueError):
+        optimizer.objective_batched(P, cfg, "nope")
+    capsys.readouterr()
+
+
+def test_objective_statistics_match_oracle(gpu, capsys):
+    """Mean objective over many independent evaluations, GPU Philox vs CPU oracle, at the YAML defaults."""
+    from mcluminescence_b200 import optimizer
+    from mcluminescence_b200.config import compose, initialize_runs
+    from mcluminescence_b200.replicas import LAB_CSV, LabTable
+    from oracle import mcl_oracle as mo
+    cfg = compose(overrides=helpers.LAB_OVERRIDES)
+    run = initialize_runs(cfg)[0]
+    p0 = np.array([run.exp_type_fp.rho_prime, run.physics_fp.E_cb, run.physics_fp.E_loc_1, run.physics_fp.E_loc_2,
+                   run.physics_fp.D0, run.physics_fp.s, run.physics_fp.b, run.physics_fp.alpha,
+                   run.exp_type_fp.holes, run.physics_fp.Retrap], dtype=float)
+    M = 64
+    g = optimizer.objective_batched(np.tile(p0[:, None], (1, M)), cfg, "tl_clbr", seed=8)
+    lt = LabTable(*LAB_CSV["tl_clbr"], helpers.DATA_ROOT)
+    reps1, segs = lt.tables(run)
+    ref = mo.run(np.tile(reps1, M), segs, int(run.exp_type_fp.steps), seed=600, parallel=True, trace=False)
+    o = np.array([lt.mse(run.exp_type_fp.N_e, ref.final_n_e[m * 11:(m + 1) * 11])[1] for m in range(M)])
+    se = np.sqrt(g.var(ddof=1) / M + o.var(ddof=1) / M)
+    assert abs(g.mean() - o.mean()) <= 4 * se, (g.mean(), o.mean(), se)
+    capsys.readouterr()
