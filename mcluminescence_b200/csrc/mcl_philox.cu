@@ -91,7 +91,7 @@ struct Holes {
 };
 
 // Warp-cooperative nearest alive hole of (x,y,z).  Returns (bits(d2) << 32 | slot) to all lanes.
-__device__ unsigned long long warp_nearest(const Holes &H, float x, float y, float z, int lane)
+__device__ unsigned long long warp_nearest(const Holes &H, float x, float y, float z, int lane, int exclude = -1)
 {
     const int G = H.G;
     int cx = min(G - 1, max(0, (int)(x * H.inv_w)));
@@ -111,7 +111,7 @@ __device__ unsigned long long warp_nearest(const Holes &H, float x, float y, flo
                 float dx = x - H.x[j], dy = y - H.y[j], dz = z - H.z[j];
                 float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                 unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
-                best = key < best ? key : best;
+                best = (key < best && j != exclude) ? key : best;
             }
         }
         best = warp_min_u64(best);
@@ -132,7 +132,7 @@ __device__ unsigned long long warp_nearest(const Holes &H, float x, float y, flo
         float dx = x - H.x[j], dy = y - H.y[j], dz = z - H.z[j];
         float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
         unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
-        best = key < best ? key : best;
+        best = (key < best && j != exclude) ? key : best;
     }
     return warp_min_u64(best);
 }
@@ -481,6 +481,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 unsigned m = __ballot_sync(0xffffffffu, best == wv);
                 int src = m ? (__ffs(m) - 1) : 0;
                 int ws_ = __shfl_sync(0xffffffffu, bslot, src);
+                __syncwarp();
                 if (lane == 0) { red_v[par][warp] = wv; red_s[par][warp] = ws_; red_h[par][warp] = ws_ >= 0 ? (int)near[ws_] : -1; }
             }
             if (warp == 0) {
@@ -562,52 +563,74 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     }
                 }
                 if (h >= n_h0) n_fill_alive--;
-                // which other electrons were cached on h (or h2)?  16 bytes of slots per load
-                bool mine = false;
-                {
-                    const uint4 *nv = reinterpret_cast<const uint4 *>(near);
-                    const int n_vec = (n_slots + PER_VEC - 1) / PER_VEC;
-                    for (int v = tid; v < n_vec; v += NT) {
-                        const uint4 w = nv[v];
-                        bool hit = vec_may_match(w, (uint32_t)h, NearT());
-                        if (h2 >= 0) hit |= vec_may_match(w, (uint32_t)h2, NearT());
-                        if (hit) {
-                            for (int k = 0; k < PER_VEC; k++) {
-                                const int sl = v * PER_VEC + k;
-                                const uint32_t nn = near[sl];
-                                if (sl != smin && (nn == (uint32_t)h || (h2 >= 0 && nn == (uint32_t)h2))) {
-                                    bool fixed = false;
-                                    if (!ever_filled) {
-                                        // no hole was ever added: the new nearest is the first remembered
-                                        // candidate that is still alive (and is not the hole dying now)
-                                        const float4 d4 = cand_d[sl];
-                                        const float dk[KC] = {d4.x, d4.y, d4.z, d4.w};
+                // Which of MY other electrons were cached on h (or h2)?  A thread owns the pairs it sweeps
+                // (q = tid, tid + NT, ...), and only the owner ever touches cr[] / near[] of a pair outside
+                // barrier-protected phases -- so re-targeting needs no CTA barrier at all.
+                int redo = -1;                      // a slot of mine that needs the warp-cooperative search
+                auto retarget = [&](int sl) {
+                    bool fixed = false;
+                    if (!ever_filled) {
+                        // no hole was ever added: the new nearest is the first remembered candidate that is
+                        // still alive (and is not the hole dying now, whose bitmap bit may not be visible yet)
+                        const float4 d4 = cand_d[sl];
+                        const float dk[KC] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-                                        for (int c = 0; c < KC; c++) {
-                                            const uint32_t j = cand_j[(size_t)sl * KC + c];
-                                            if (!fixed && j != NEAR_DEAD && j != (uint32_t)h && ((hole_bm[j >> 5] >> (j & 31)) & 1u)) {
-                                                cr[sl] = dk[c]; near[sl] = (NearT)j; fixed = true;
-                                            }
-                                        }
-                                    }
-                                    if (!fixed) { flist[atomicAdd(&s_nflag, 1)] = sl; mine = true; }
+                        for (int c = 0; c < KC; c++) {
+                            const uint32_t j = cand_j[(size_t)sl * KC + c];
+                            if (!fixed && j != NEAR_DEAD && j != (uint32_t)h && ((hole_bm[j >> 5] >> (j & 31)) & 1u)) {
+                                cr[sl] = dk[c]; near[sl] = (NearT)j; fixed = true;
+                            }
+                        }
+                    }
+                    return fixed;
+                };
+                auto scan = [&](auto two_targets) {
+                    constexpr bool TWO = decltype(two_targets)::value;
+                    for (int q = tid; q < n_pairs; q += NT) {
+                        uint32_t n0, n1;
+                        if (sizeof(NearT) == 2) {
+                            const uint32_t w = reinterpret_cast<const uint32_t *>(near)[q];
+                            n0 = w & 0xffffu; n1 = w >> 16;
+                        } else {
+                            const uint2 w = reinterpret_cast<const uint2 *>(near)[q];
+                            n0 = w.x; n1 = w.y;
+                        }
+                        const bool m0 = (n0 == (uint32_t)h) || (TWO && n0 == (uint32_t)h2);
+                        const bool m1 = (n1 == (uint32_t)h) || (TWO && n1 == (uint32_t)h2);
+                        if (m0 || m1) {
+#pragma unroll
+                            for (int k = 0; k < 2; k++) {
+                                const int sl = 2 * q + k;
+                                if ((k ? m1 : m0) && sl != smin && !retarget(sl)) {
+                                    // rare: park it (+inf keeps it out of every clock) until the warp search below
+                                    if (redo >= 0) cr[sl] = -1.0f;      // more than one: mark, found again below
+                                    else redo = sl;
                                 }
                             }
                         }
                     }
-                }
-                int any_flag;
-                if (NT > 32) any_flag = __syncthreads_or(mine);       // ===== B2
-                else { __syncwarp(); any_flag = __any_sync(0xffffffffu, mine); }
-                if (any_flag) {
-                    const int nflag = s_nflag;
-                    for (int f = warp; f < nflag; f += NW) {
-                        int s = flist[f];
-                        unsigned long long b = warp_nearest(H, ex[s], ey[s], ez[s], lane);
-                        if (lane == 0) { cr[s] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[s] = (NearT)(uint32_t)b; }
+                };
+                if (h2 >= 0) scan(std::true_type{}); else scan(std::false_type{});
+                // Exhausted lists and fill mode (new holes become visible on a re-search, engine.py:171-175):
+                // the owner's WARP searches the cell grid cooperatively; still no CTA barrier.
+                {
+                    unsigned need = __ballot_sync(0xffffffffu, redo >= 0);
+                    while (need) {
+                        const int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int sl = __shfl_sync(0xffffffffu, redo, src);
+                        unsigned long long b = warp_nearest(H, ex[sl], ey[sl], ez[sl], lane, h);
+                        if (lane == src) {
+                            cr[sl] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[sl] = (NearT)(uint32_t)b;
+                            // further parked slots of this lane were marked with cr = -1
+                            redo = -1;
+                            for (int q = tid; q < n_pairs && redo < 0; q += NT) {
+                                if (cr[2 * q] == -1.0f) redo = 2 * q;
+                                else if (cr[2 * q + 1] == -1.0f) redo = 2 * q + 1;
+                            }
+                        }
+                        need |= __ballot_sync(0xffffffffu, lane == src && redo >= 0) ;
                     }
-                    cta_sync<NT>();                           // ===== B3
-                    if (tid == 0) s_nflag = 0;
                 }
                 // ---------------- compaction: keep tombstones below 1/8 of the slots in use
                 if ((n_slots - n_e) * 8 > n_slots && n_slots >= 64) {
