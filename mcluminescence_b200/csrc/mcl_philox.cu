@@ -447,15 +447,17 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             float best = F_INF; int bslot = -1;
             const int n_pairs = (n_slots + 1) >> 1;
             const float2 *cr2 = reinterpret_cast<const float2 *>(cr);
-            auto pair_loop = [&](auto with_cb) {
+            auto pair_loop = [&](auto with_cb, auto one_channel) {
                 constexpr bool CB = decltype(with_cb)::value;
+                constexpr bool ONE = decltype(one_channel)::value;     // both tunnelling channels identical
 #pragma unroll (NT >= 256 ? 2 : 1)
                 for (int q = tid; q < n_pairs; q += NT) {
                     const float2 c = cr2[q];
                     uint32_t c0 = (uint32_t)q, c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);
                     philox4x32_10(c0, c1, c2, c3, K);
-                    float a0 = ((c0 < thr) ? A2 : A1) - c.x;
-                    float a1 = ((c2 < thr) ? A2 : A1) - c.y;
+                    // the selector draws (c0, c2) pick the channel; with identical channels the pick is moot
+                    float a0 = (ONE ? A1 : ((c0 < thr) ? A2 : A1)) - c.x;
+                    float a1 = (ONE ? A1 : ((c2 < thr) ? A2 : A1)) - c.y;
                     float le0 = lg2_fast(-lg2_fast(u01(c1)));
                     float le1 = lg2_fast(-lg2_fast(u01(c3)));
                     float l0, l1;
@@ -474,7 +476,8 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     if (l1 < best) { best = l1; bslot = 2 * q + 1; }
                 }
             };
-            if (has_cb) pair_loop(std::true_type{}); else pair_loop(std::false_type{});
+            if (A1 == A2) { if (has_cb) pair_loop(std::true_type{}, std::true_type{}); else pair_loop(std::false_type{}, std::true_type{}); }
+            else          { if (has_cb) pair_loop(std::true_type{}, std::false_type{}); else pair_loop(std::false_type{}, std::false_type{}); }
             // warp argmin -> one row per warp
             {
                 float wv = warp_min_f32(best);
@@ -791,7 +794,8 @@ static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override)
     else if (cap_e <= 4096) nt = 128;
     else nt = 256;
     if (const char *env = getenv("MCL_PHILOX_NT")) nt_override = atoi(env);     // tuning knob
-    if (nt_override == 32 || nt_override == 64 || nt_override == 128 || nt_override == 256 || nt_override == 512)
+    if (nt_override == 32 || nt_override == 64 || nt_override == 128 || nt_override == 256 || nt_override == 320 ||
+        nt_override == 384 || nt_override == 512)
         nt = nt_override;
     pl.nt = nt;
     return pl;
@@ -829,6 +833,8 @@ cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_
         MCL_CASE(64, 16);
         MCL_CASE(128, 8);
         MCL_CASE(256, 3);
+        MCL_CASE(320, 3);
+        MCL_CASE(384, 3);
         default: break;
     }
     return pl.near16 ? launch_one<512, 2, uint16_t>(p, K, cfg, pl.smem, stream)
