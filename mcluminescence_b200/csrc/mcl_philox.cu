@@ -46,6 +46,7 @@ struct Cfg {
     int g_max;         // largest grid edge the slab has room for
     int cap_cells;     // g_max^3 + 1
     int bm_words;      // smem words of the initial-hole alive bitmap
+    size_t off_holes;  // byte offset of the hole table inside the slab (16-byte aligned)
     size_t off_cand;   // byte offset of the candidate lists inside the slab
 };
 
@@ -84,7 +85,7 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 }
 
 struct Holes {
-    float *x, *y, *z;
+    float4 *pos;                 // (x, y, z, original index bits); x = 1e30 marks a dead hole
     const int *cell_start;
     int G, n_h0, n_slots;        // n_slots = high-water mark including the fill region
     float inv_w, w;
@@ -108,7 +109,8 @@ __device__ unsigned long long warp_nearest(const Holes &H, float x, float y, flo
             int c = (ax * G + ay) * G + az;
             int j0 = H.cell_start[c], j1 = H.cell_start[c + 1];
             for (int j = j0; j < j1; j++) {
-                float dx = x - H.x[j], dy = y - H.y[j], dz = z - H.z[j];
+                const float4 hp = H.pos[j];
+                float dx = x - hp.x, dy = y - hp.y, dz = z - hp.z;
                 float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                 unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
                 best = (key < best && j != exclude) ? key : best;
@@ -129,7 +131,8 @@ __device__ unsigned long long warp_nearest(const Holes &H, float x, float y, flo
     }
     // holes added by fills live outside the grid
     for (int j = H.n_h0 + lane; j < H.n_slots; j += 32) {
-        float dx = x - H.x[j], dy = y - H.y[j], dz = z - H.z[j];
+        const float4 hp = H.pos[j];
+        float dx = x - hp.x, dy = y - hp.y, dz = z - hp.z;
         float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
         unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
         best = (key < best && j != exclude) ? key : best;
@@ -160,7 +163,8 @@ __device__ void warp_nearest_k(const Holes &H, float x, float y, float z, int la
             int c = (ax * G + ay) * G + az;
             int j0 = H.cell_start[c], j1 = H.cell_start[c + 1];
             for (int j = j0; j < j1; j++) {
-                float dx = x - H.x[j], dy = y - H.y[j], dz = z - H.z[j];
+                const float4 hp = H.pos[j];
+                float dx = x - hp.x, dy = y - hp.y, dz = z - hp.z;
                 float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                 unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
                 if (key < k3) {
@@ -205,25 +209,11 @@ template <typename NearT> struct NearTraits;
 template <> struct NearTraits<uint16_t> { static constexpr uint32_t DEAD = 0xffffu; static constexpr int PER_VEC = 8; };
 template <> struct NearTraits<uint32_t> { static constexpr uint32_t DEAD = 0xffffffffu; static constexpr int PER_VEC = 4; };
 
-// candidate test of one 16-byte vector of slots against hole h (and h2): may report false
-// positives (borrow of the zero-halfword trick), never false negatives; the slow path re-checks.
-__device__ __forceinline__ bool vec_may_match(const uint4 w, uint32_t h, uint16_t)
-{
-    const uint32_t hh = h * 0x00010001u;
-    auto zh = [](uint32_t t) { return (t - 0x00010001u) & ~t & 0x80008000u; };
-    return (zh(w.x ^ hh) | zh(w.y ^ hh) | zh(w.z ^ hh) | zh(w.w ^ hh)) != 0u;
-}
-__device__ __forceinline__ bool vec_may_match(const uint4 w, uint32_t h, uint32_t)
-{
-    return (w.x == h) | (w.y == h) | (w.z == h) | (w.w == h);
-}
-
 template <int NT, int MINB, typename NearT>
 __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, const RoundKeys K, const Cfg cfg)
 {
     constexpr int NW = NT / 32;
     constexpr uint32_t NEAR_DEAD = NearTraits<NearT>::DEAD;
-    constexpr int PER_VEC = NearTraits<NearT>::PER_VEC;
     const int r = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const mcl_replica rp = p.replicas[r];
@@ -247,9 +237,8 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     unsigned char *ws = p.ws + (size_t)r * p.ws_stride;
     const size_t ce = (size_t)p.cap_e, ch = (size_t)p.cap_h;
     float *ex = reinterpret_cast<float *>(ws), *ey = ex + ce, *ez = ex + 2 * ce;
-    float *hx = ex + 3 * ce, *hy = hx + ch, *hz = hx + 2 * ch;
-    int *hid = reinterpret_cast<int *>(hx + 3 * ch);                  // [cap_h]  init only
-    int *cell_start = hid + ch;                                       // [cap_cells]
+    float4 *hpos = reinterpret_cast<float4 *>(ws + cfg.off_holes);    // [cap_h] (x, y, z, original index)
+    int *cell_start = reinterpret_cast<int *>(hpos + ch);             // [cap_cells]
     int *cell_fill = cell_start + cfg.cap_cells;                      // [cap_cells] init only
     int *flist = cell_fill + cfg.cap_cells;                           // [cap_e]
     float4 *cand_d = reinterpret_cast<float4 *>(ws + cfg.off_cand);   // [cap_e] cr of the KC nearest initial holes
@@ -264,7 +253,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     if (n_e > 0 && n_h0 <= 0) status = MCL_ERR_NOHOLES;
 
     Holes H;
-    H.x = hx; H.y = hy; H.z = hz; H.cell_start = cell_start; H.n_h0 = n_h0; H.n_slots = n_h0;
+    H.pos = hpos; H.cell_start = cell_start; H.n_h0 = n_h0; H.n_slots = n_h0;
     H.G = max(1, min(cfg.g_max, (int)cbrtf((float)n_h0 * (1.0f / 3.0f))));
     H.w = bnd_s / (float)H.G; H.inv_w = (float)H.G / bnd_s;
     const int n_cells = H.G * H.G * H.G;
@@ -311,40 +300,165 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             float x, y, z; hole_pos(j, x, y, z);
             int c = cell_of(x, y, z);
             int q = cell_start[c] + atomicAdd(&cell_fill[c], 1);
-            hx[q] = x; hy[q] = y; hz[q] = z; hid[q] = j;
+            hpos[q] = make_float4(x, y, z, __int_as_float(j));
         }
         cta_sync<NT>();
         // deterministic order inside each cell (by original index): atomics above are unordered
         for (int c = tid; c < n_cells; c += NT) {
             int j0 = cell_start[c], j1 = cell_start[c + 1];
             for (int a = j0 + 1; a < j1; a++) {
-                int id = hid[a]; float x = hx[a], y = hy[a], z = hz[a];
+                const float4 v = hpos[a];
+                const int id = __float_as_int(v.w);
                 int b = a - 1;
-                while (b >= j0 && hid[b] > id) { hid[b + 1] = hid[b]; hx[b + 1] = hx[b]; hy[b + 1] = hy[b]; hz[b + 1] = hz[b]; b--; }
-                hid[b + 1] = id; hx[b + 1] = x; hy[b + 1] = y; hz[b + 1] = z;
+                while (b >= j0 && __float_as_int(hpos[b].w) > id) { hpos[b + 1] = hpos[b]; b--; }
+                hpos[b + 1] = v;
             }
         }
-        // electrons
-        for (int i = tid; i < n_e; i += NT) {
+        cta_sync<NT>();
+        // ---------------- electrons, stored in grid-cell order (slot order carries no meaning in Philox mode;
+        // it only has to be deterministic).  Grouping them by cell lets one warp fetch the ~95 holes around a
+        // cell ONCE and serve every electron of the cell from registers.
+        auto electron_pos = [&](int i, float &x, float &y, float &z) {
             uint32_t c0 = (uint32_t)i, c1 = 0u, c2 = rid_lo, c3 = rid_hi | (DOM_SEED_E << 28);
             philox4x32_10(c0, c1, c2, c3, K);
-            ex[i] = u01(c0) * core_s; ey[i] = u01(c1) * core_s; ez[i] = u01(c2) * core_s;
+            x = u01(c0) * core_s; y = u01(c1) * core_s; z = u01(c2) * core_s;
+        };
+        int *e_start = cell_fill;                 // per-cell electron counts -> exclusive starts
+        int *e_id = flist;                        // original electron index held by every sorted slot
+        for (int c = tid; c <= n_cells; c += NT) e_start[c] = 0;
+        for (int i = tid; i < n_e; i += NT) e_id[i] = -1;
+        cta_sync<NT>();
+        for (int i = tid; i < n_e; i += NT) {
+            float x, y, z; electron_pos(i, x, y, z);
+            atomicAdd(&e_start[cell_of(x, y, z)], 1);
         }
         cta_sync<NT>();
-        // Box._rebuild (engine.py:113-119): nearest hole of every electron, one warp per electron
-        for (int i = warp; i < n_e; i += NW) {
+        if (warp == 0) {
+            int run = 0;
+            for (int base = 0; base < n_cells; base += 32) {
+                int c = base + lane;
+                int v = c < n_cells ? e_start[c] : 0;
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                if (c < n_cells) e_start[c] = run + inc - v;
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) e_start[n_cells] = run;
+        }
+        cta_sync<NT>();
+        for (int i = tid; i < n_e; i += NT) {     // unordered scatter into the cell's range ...
+            float x, y, z; electron_pos(i, x, y, z);
+            int q = e_start[cell_of(x, y, z)];
+            while (atomicCAS(&e_id[q], -1, i) != -1) q++;
+        }
+        cta_sync<NT>();
+        for (int c = tid; c < n_cells; c += NT) { // ... then a tiny insertion sort per cell makes it deterministic
+            const int j0 = e_start[c], j1 = e_start[c + 1];
+            for (int a = j0 + 1; a < j1; a++) {
+                const int id = e_id[a];
+                int b = a - 1;
+                while (b >= j0 && e_id[b] > id) { e_id[b + 1] = e_id[b]; b--; }
+                e_id[b + 1] = id;
+            }
+        }
+        cta_sync<NT>();
+        for (int i = tid; i < n_e; i += NT) {
+            float x, y, z; electron_pos(e_id[i], x, y, z);
+            ex[i] = x; ey[i] = y; ez[i] = z;
+        }
+        cta_sync<NT>();
+        // ---------------- Box._rebuild (engine.py:113-119): the KC nearest holes of every electron.
+        // One warp per occupied cell: lanes 0..26 read the hole ranges of the 27 surrounding cells, the
+        // (<= 128) holes are spread 4 per lane and loaded once, then each electron of the cell needs 4
+        // distance evaluations per lane and KC warp-min rounds.
+        auto store_lists = [&](int i, const float d2[KC], const int jj[KC]) {      // lane 0
+            float d[KC];
+#pragma unroll
+            for (int k = 0; k < KC; k++) {
+                d[k] = jj[k] >= 0 ? sqrtf(d2[k]) : F_INF;
+                cand_j[(size_t)i * KC + k] = jj[k] >= 0 ? (NearT)jj[k] : (NearT)NEAR_DEAD;
+            }
+            cand_d[i] = make_float4(d[0], d[1], d[2], d[3]);
+            cr[i] = d[0]; near[i] = jj[0] >= 0 ? (NearT)jj[0] : (NearT)NEAR_DEAD;
+        };
+        auto slow_lists = [&](int i) {            // generic ring search (crowded cell or a list that is not yet exact)
             unsigned long long b[KC];
             warp_nearest_k(H, ex[i], ey[i], ez[i], lane, b);
-            if (lane == 0) {
-                float d[KC];
+            float d2[KC]; int jj[KC];
 #pragma unroll
-                for (int k = 0; k < KC; k++) {
-                    const bool ok = b[k] != ~0ull;
-                    d[k] = ok ? sqrtf(__uint_as_float((uint32_t)(b[k] >> 32))) : F_INF;
-                    cand_j[(size_t)i * KC + k] = ok ? (NearT)(uint32_t)b[k] : (NearT)NEAR_DEAD;
+            for (int k = 0; k < KC; k++) {
+                const bool ok = b[k] != ~0ull;
+                d2[k] = ok ? __uint_as_float((uint32_t)(b[k] >> 32)) : F_INF;
+                jj[k] = ok ? (int)(uint32_t)b[k] : -1;
+            }
+            if (lane == 0) store_lists(i, d2, jj);
+        };
+        const int G = H.G;
+        for (int c = warp; c < n_cells; c += NW) {
+            const int i0 = e_start[c], i1 = e_start[c + 1];
+            if (i0 == i1) continue;                                     // warp-uniform
+            const int ax = c / (G * G), ay = (c / G) % G, az = c % G;
+            const int nx_ = ax + lane / 9 - 1, ny_ = ay + (lane / 3) % 3 - 1, nz_ = az + lane % 3 - 1;
+            const bool valid = lane < 27 && (unsigned)nx_ < (unsigned)G && (unsigned)ny_ < (unsigned)G && (unsigned)nz_ < (unsigned)G;
+            const int nc = valid ? (nx_ * G + ny_) * G + nz_ : 0;
+            const int j0 = valid ? cell_start[nc] : 0;
+            const int cnt = valid ? cell_start[nc + 1] - j0 : 0;
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            const int total = __shfl_sync(0xffffffffu, inc, 31);
+            const int off = inc - cnt;
+            if (total > 128) { for (int i = i0; i < i1; i++) slow_lists(i); continue; }
+            float4 hp[4]; int hj[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int item = lane + 32 * k;
+                int pos = 0;                                            // last lane whose range starts at or before item
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    const int t = __shfl_sync(0xffffffffu, off, min(pos + sft, 31));
+                    if (pos + sft < 32 && t <= item) pos += sft;
                 }
-                cand_d[i] = make_float4(d[0], d[1], d[2], d[3]);
-                cr[i] = d[0]; near[i] = b[0] != ~0ull ? (NearT)(uint32_t)b[0] : (NearT)NEAR_DEAD;
+                const int jbase = __shfl_sync(0xffffffffu, j0, pos), obase = __shfl_sync(0xffffffffu, off, pos);
+                const bool on = item < total;
+                hj[k] = on ? jbase + (item - obase) : -1;
+                hp[k] = on ? hpos[hj[k]] : make_float4(DEAD_X, 0.f, 0.f, 0.f);
+            }
+            // everything outside the 3x3x3 block is at least this far from an electron of cell c
+            const float lo_x = (ax > 0) ? (ax - 1) * H.w : -F_INF, hi_x = (ax < G - 1) ? (ax + 2) * H.w : F_INF;
+            const float lo_y = (ay > 0) ? (ay - 1) * H.w : -F_INF, hi_y = (ay < G - 1) ? (ay + 2) * H.w : F_INF;
+            const float lo_z = (az > 0) ? (az - 1) * H.w : -F_INF, hi_z = (az < G - 1) ? (az + 2) * H.w : F_INF;
+            for (int i = i0; i < i1; i++) {
+                const float x = ex[i], y = ey[i], z = ez[i];
+                float d2[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float dx = x - hp[k].x, dy = y - hp[k].y, dz = z - hp[k].z;
+                    d2[k] = fmaf(dx, dx, fmaf(dy, dy, dz * dz));                   // inf for an unused register
+                }
+                float od[KC]; int oj[KC];
+#pragma unroll
+                for (int r_ = 0; r_ < KC; r_++) {
+                    const float m = fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3]));
+                    const float g_ = warp_min_f32(m);
+                    const unsigned who = __ballot_sync(0xffffffffu, m == g_);
+                    const int owner = who ? __ffs(who) - 1 : 0;
+                    int mine_j = -1;
+                    if (lane == owner) {
+                        int ksel = -1;
+#pragma unroll
+                        for (int k = 3; k >= 0; k--) if (d2[k] == m) ksel = k;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) if (k == ksel) { mine_j = hj[k]; d2[k] = F_INF; }
+                    }
+                    oj[r_] = (g_ < F_INF) ? __shfl_sync(0xffffffffu, mine_j, owner) : -1;
+                    od[r_] = g_;
+                }
+                // a face of the block that lies inside the grid limits how far the list is provably complete
+                const float bound = fminf(fminf(fminf(x - lo_x, hi_x - x), fminf(y - lo_y, hi_y - y)), fminf(z - lo_z, hi_z - z));
+                if (od[KC - 1] <= bound * bound) { if (lane == 0) store_lists(i, od, oj); }
+                else slow_lists(i);
             }
         }
         cta_sync<NT>();
@@ -554,10 +668,10 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 if (ever_filled) {
                     // stale-cache mode: the reference also refreshes electrons cached on the hole that
                     // FOLLOWS the removed one in index order (shift-then-mask, engine.py:168-171)
-                    for (int j = h + 1; j < H.n_slots; j++) if (hx[j] < 1e29f) { h2 = j; break; }
+                    for (int j = h + 1; j < H.n_slots; j++) if (hpos[j].x < 1e29f) { h2 = j; break; }
                 }
                 if (tid == 0) {
-                    hx[h] = DEAD_X;
+                    hpos[h].x = DEAD_X;
                     if (h < n_h0) hole_bm[h >> 5] &= ~(1u << (h & 31));
                     if (hist_on && p.hist_events) {
                         // edges up to t_cur have been passed: the event sits in the bin before the cursor
@@ -703,7 +817,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         hs = -1;
                         for (int base = n_h0; base < H.n_slots && hs < 0; base += 32) {
                             int j = base + lane;
-                            unsigned m = __ballot_sync(0xffffffffu, j < H.n_slots && !(hx[j] < 1e29f));
+                            unsigned m = __ballot_sync(0xffffffffu, j < H.n_slots && !(hpos[j].x < 1e29f));
                             if (m) hs = base + __ffs(m) - 1;
                         }
                     }
@@ -716,7 +830,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     if (lane == 0) {
                         ex[es] = nx; ey[es] = ny; ez[es] = nz;
                         cr[es] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[es] = (NearT)(uint32_t)b;
-                        hx[hs] = qx; hy[hs] = qy; hz[hs] = qz;
+                        hpos[hs] = make_float4(qx, qy, qz, __int_as_float(hs));
                     }
                 }
                 if (append_e) n_slots++;
@@ -771,7 +885,7 @@ static int grid_edge_max(int n_h0_max)
     return g < 1 ? 1 : g;
 }
 
-struct PhiloxPlan { int nt; int cap_slots; int g_max; int cap_cells; int bm_words; size_t smem; size_t off_cand; size_t stride; bool near16; };
+struct PhiloxPlan { int nt; int cap_slots; int g_max; int cap_cells; int bm_words; size_t smem; size_t off_holes; size_t off_cand; size_t stride; bool near16; };
 
 static int g_nt_override = 0;
 void philox_set_block_threads(int nt) { g_nt_override = nt; }
@@ -785,7 +899,8 @@ static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override)
     pl.near16 = cap_h <= 65534;
     pl.bm_words = (cap_h + 31) / 32;
     pl.smem = (size_t)pl.cap_slots * (4 + (pl.near16 ? 2 : 4)) + 4 * (size_t)pl.bm_words;
-    size_t b = sizeof(float) * 3 * ((size_t)cap_e + (size_t)cap_h) + sizeof(int) * ((size_t)cap_h + 2 * (size_t)pl.cap_cells + (size_t)cap_e);
+    pl.off_holes = align_up(sizeof(float) * 3 * (size_t)cap_e, 16);
+    size_t b = pl.off_holes + 16 * (size_t)cap_h + sizeof(int) * (2 * (size_t)pl.cap_cells + (size_t)cap_e);
     pl.off_cand = align_up(b, 16);
     pl.stride = align_up(pl.off_cand + (size_t)cap_e * (16 + 4 * (pl.near16 ? 2 : 4)), 256);
     int nt;
@@ -818,7 +933,7 @@ static cudaError_t launch_one(const LaunchParams &p, const RoundKeys &K, const C
 cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_slots*/)
 {
     PhiloxPlan pl = make_plan(p.cap_e, p.cap_h, g_nt_override);
-    Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.off_cand};
+    Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.off_holes, pl.off_cand};
     RoundKeys K;
     uint64_t s = mix64(p.seed);
     uint32_t k0 = (uint32_t)s, k1 = (uint32_t)(s >> 32);
