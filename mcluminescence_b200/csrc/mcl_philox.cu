@@ -209,11 +209,12 @@ template <typename NearT> struct NearTraits;
 template <> struct NearTraits<uint16_t> { static constexpr uint32_t DEAD = 0xffffu; static constexpr int PER_VEC = 8; };
 template <> struct NearTraits<uint32_t> { static constexpr uint32_t DEAD = 0xffffffffu; static constexpr int PER_VEC = 4; };
 
-template <int NT, int MINB, typename NearT>
+template <int NT, int MINB, typename NearT, int PPC>
 __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, const RoundKeys K, const Cfg cfg)
 {
     constexpr int NW = NT / 32;
     constexpr uint32_t NEAR_DEAD = NearTraits<NearT>::DEAD;
+    constexpr int SPC = 2 * PPC;              // slots per chunk: a thread owns whole chunks (chunk b -> thread b % NT)
     const int r = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const mcl_replica rp = p.replicas[r];
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     const float bnd_s = (float)(rp.side * rp.boundary_factor * rp.alpha * L2E);
     const int n_h0 = rp.n_h0;
     int n_e = rp.n_e0;
-    if (n_e > cfg.cap_slots - 2 || n_e > p.cap_e || n_h0 > p.cap_h) status = MCL_ERR_CAPACITY;
+    if (n_e > cfg.cap_slots - 4 || n_e > p.cap_e || n_h0 > p.cap_h) status = MCL_ERR_CAPACITY;
     if (n_e > 0 && n_h0 <= 0) status = MCL_ERR_NOHOLES;
 
     Holes H;
@@ -559,35 +560,45 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
 
             // ---------------- per-electron clocks + running argmin
             float best = F_INF; int bslot = -1;
-            const int n_pairs = (n_slots + 1) >> 1;
-            const float2 *cr2 = reinterpret_cast<const float2 *>(cr);
+            // A thread owns whole CHUNKS of SPC slots (chunk b = slots SPC*b.. belongs to thread b % NT).  With
+            // PPC = 2 one 16-byte load feeds two independent Philox calls and the post-event scan reads the
+            // chunk's four nearest-hole slots with one load; PPC = 1 keeps the granularity fine for small boxes.
+            const int n_chunks = (n_slots + SPC - 1) / SPC;
             auto pair_loop = [&](auto with_cb, auto one_channel) {
                 constexpr bool CB = decltype(with_cb)::value;
                 constexpr bool ONE = decltype(one_channel)::value;     // both tunnelling channels identical
-#pragma unroll (NT >= 256 ? 2 : 1)
-                for (int q = tid; q < n_pairs; q += NT) {
-                    const float2 c = cr2[q];
-                    uint32_t c0 = (uint32_t)q, c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);
-                    philox4x32_10(c0, c1, c2, c3, K);
-                    // the selector draws (c0, c2) pick the channel; with identical channels the pick is moot
-                    float a0 = (ONE ? A1 : ((c0 < thr) ? A2 : A1)) - c.x;
-                    float a1 = (ONE ? A1 : ((c2 < thr) ? A2 : A1)) - c.y;
-                    float le0 = lg2_fast(-lg2_fast(u01(c1)));
-                    float le1 = lg2_fast(-lg2_fast(u01(c3)));
-                    float l0, l1;
-                    if (CB) {
-                        // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
-                        float m0 = fmaxf(a0, g), m1 = fmaxf(a1, g);
-                        float k0 = m0 + lg2_fast(1.0f + ex2_fast(-fabsf(a0 - g)));
-                        float k1 = m1 + lg2_fast(1.0f + ex2_fast(-fabsf(a1 - g)));
-                        l0 = (le0 - k0) + (c.x - c.x);
-                        l1 = (le1 - k1) + (c.y - c.y);
+                for (int b = tid; b < n_chunks; b += NT) {
+                    float cs[SPC];
+                    if (PPC == 2) {
+                        const float4 cq = reinterpret_cast<const float4 *>(cr)[b];
+                        cs[0] = cq.x; cs[1] = cq.y; cs[SPC - 2] = cq.z; cs[SPC - 1] = cq.w;
                     } else {
-                        l0 = le0 - a0;
-                        l1 = le1 - a1;
+                        const float2 cq = reinterpret_cast<const float2 *>(cr)[b];
+                        cs[0] = cq.x; cs[1] = cq.y;
                     }
-                    if (l0 < best) { best = l0; bslot = 2 * q; }
-                    if (l1 < best) { best = l1; bslot = 2 * q + 1; }
+                    float l[SPC];
+#pragma unroll
+                    for (int i = 0; i < PPC; i++) {
+                        uint32_t c0 = (uint32_t)(PPC * b + i), c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);
+                        philox4x32_10(c0, c1, c2, c3, K);
+                        // the selector draws (c0, c2) pick the channel; with identical channels the pick is moot
+                        const float a0 = (ONE ? A1 : ((c0 < thr) ? A2 : A1)) - cs[2 * i];
+                        const float a1 = (ONE ? A1 : ((c2 < thr) ? A2 : A1)) - cs[2 * i + 1];
+                        const float le0 = lg2_fast(-lg2_fast(u01(c1)));
+                        const float le1 = lg2_fast(-lg2_fast(u01(c3)));
+                        if (CB) {
+                            // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
+                            const float k0 = fmaxf(a0, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a0 - g)));
+                            const float k1 = fmaxf(a1, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a1 - g)));
+                            l[2 * i] = (le0 - k0) + (cs[2 * i] - cs[2 * i]);
+                            l[2 * i + 1] = (le1 - k1) + (cs[2 * i + 1] - cs[2 * i + 1]);
+                        } else {
+                            l[2 * i] = le0 - a0;
+                            l[2 * i + 1] = le1 - a1;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < SPC; i++) if (l[i] < best) { best = l[i]; bslot = SPC * b + i; }
                 }
             };
             if (A1 == A2) { if (has_cb) pair_loop(std::true_type{}, std::true_type{}); else pair_loop(std::false_type{}, std::true_type{}); }
@@ -662,7 +673,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 // ---------------- Box.remove_pair (engine.py:154-175)
                 ev = 1;
                 const int h = hmin;                                    // nearest hole of the winner (read before B1)
-                if (tid == ((smin >> 1) % NT)) { cr[smin] = F_INF; near[smin] = (NearT)NEAR_DEAD; }   // owner tombstones it
+                if (tid == ((smin / SPC) % NT)) { cr[smin] = F_INF; near[smin] = (NearT)NEAR_DEAD; }   // owner tombstones it
                 n_e--;
                 int h2 = -1;
                 if (ever_filled) {
@@ -703,23 +714,32 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 };
                 auto scan = [&](auto two_targets) {
                     constexpr bool TWO = decltype(two_targets)::value;
-                    for (int q = tid; q < n_pairs; q += NT) {
-                        uint32_t n0, n1;
+                    for (int b = tid; b < n_chunks; b += NT) {
+                        bool hit;
+                        constexpr int NWORD = SPC * (int)sizeof(NearT) / 4;       // 32-bit words of near[] per chunk
+                        uint32_t w[NWORD];
+                        if (NWORD == 4) { const uint4 v = reinterpret_cast<const uint4 *>(near)[b]; w[0] = v.x; w[1 % NWORD] = v.y; w[2 % NWORD] = v.z; w[3 % NWORD] = v.w; }
+                        else if (NWORD == 2) { const uint2 v = reinterpret_cast<const uint2 *>(near)[b]; w[0] = v.x; w[1 % NWORD] = v.y; }
+                        else w[0] = reinterpret_cast<const uint32_t *>(near)[b];
                         if (sizeof(NearT) == 2) {
-                            const uint32_t w = reinterpret_cast<const uint32_t *>(near)[q];
-                            n0 = w & 0xffffu; n1 = w >> 16;
-                        } else {
-                            const uint2 w = reinterpret_cast<const uint2 *>(near)[q];
-                            n0 = w.x; n1 = w.y;
-                        }
-                        const bool m0 = (n0 == (uint32_t)h) || (TWO && n0 == (uint32_t)h2);
-                        const bool m1 = (n1 == (uint32_t)h) || (TWO && n1 == (uint32_t)h2);
-                        if (m0 || m1) {
+                            // 16-bit slots: zero-halfword test (false positives possible, re-checked below)
+                            auto zh = [](uint32_t t) { return (t - 0x00010001u) & ~t & 0x80008000u; };
+                            const uint32_t hh = (uint32_t)h * 0x00010001u, hh2 = (uint32_t)h2 * 0x00010001u;
+                            uint32_t z = 0u;
 #pragma unroll
-                            for (int k = 0; k < 2; k++) {
-                                const int sl = 2 * q + k;
-                                if ((k ? m1 : m0) && sl != smin && !retarget(sl)) {
-                                    // rare: park it (+inf keeps it out of every clock) until the warp search below
+                            for (int k = 0; k < NWORD; k++) { z |= zh(w[k] ^ hh); if (TWO) z |= zh(w[k] ^ hh2); }
+                            hit = z != 0u;
+                        } else {
+                            hit = false;
+#pragma unroll
+                            for (int k = 0; k < NWORD; k++) { hit |= (w[k] == (uint32_t)h); if (TWO) hit |= (w[k] == (uint32_t)h2); }
+                        }
+                        if (hit) {
+                            for (int k = 0; k < SPC; k++) {
+                                const int sl = SPC * b + k;
+                                const uint32_t nn = near[sl];
+                                if ((nn == (uint32_t)h || (TWO && nn == (uint32_t)h2)) && sl != smin && !retarget(sl)) {
+                                    // rare: park it until the warp search below
                                     if (redo >= 0) cr[sl] = -1.0f;      // more than one: mark, found again below
                                     else redo = sl;
                                 }
@@ -741,10 +761,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                             cr[sl] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[sl] = (NearT)(uint32_t)b;
                             // further parked slots of this lane were marked with cr = -1
                             redo = -1;
-                            for (int q = tid; q < n_pairs && redo < 0; q += NT) {
-                                if (cr[2 * q] == -1.0f) redo = 2 * q;
-                                else if (cr[2 * q + 1] == -1.0f) redo = 2 * q + 1;
-                            }
+                            for (int b = tid; b < n_chunks && redo < 0; b += NT)
+                                for (int k = 0; k < SPC && redo < 0; k++)
+                                    if (cr[SPC * b + k] == -1.0f) redo = SPC * b + k;
                         }
                         need |= __ballot_sync(0xffffffffu, lane == src && redo >= 0) ;
                     }
@@ -801,7 +820,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 int es = -1;
                 if (n_e == n_slots) es = n_slots;             // no tombstone to reuse
                 const bool append_e = (es >= 0);
-                if (append_e && es >= cfg.cap_slots - 1) { status = MCL_ERR_CAPACITY; break; }
+                if (append_e && es >= cfg.cap_slots - 4) { status = MCL_ERR_CAPACITY; break; }
                 const bool append_h = (n_fill_alive == H.n_slots - n_h0);
                 if (append_h && H.n_slots >= p.cap_h) { status = MCL_ERR_CAPACITY; break; }
                 if (warp == 0) {
@@ -909,8 +928,7 @@ static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override)
     else if (cap_e <= 4096) nt = 128;
     else nt = 256;
     if (const char *env = getenv("MCL_PHILOX_NT")) nt_override = atoi(env);     // tuning knob
-    if (nt_override == 32 || nt_override == 64 || nt_override == 128 || nt_override == 256 || nt_override == 320 ||
-        nt_override == 384 || nt_override == 512)
+    if (nt_override == 32 || nt_override == 64 || nt_override == 128 || nt_override == 256 || nt_override == 512)
         nt = nt_override;
     pl.nt = nt;
     return pl;
@@ -921,12 +939,12 @@ size_t philox_ws_stride(int cap_e, int cap_h)
     return make_plan(cap_e, cap_h, 0).stride;
 }
 
-template <int NT, int MINB, typename NearT>
+template <int NT, int MINB, typename NearT, int PPC>
 static cudaError_t launch_one(const LaunchParams &p, const RoundKeys &K, const Cfg &cfg, size_t smem, cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(philox_kernel<NT, MINB, NearT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(philox_kernel<NT, MINB, NearT, PPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    philox_kernel<NT, MINB, NearT><<<p.n_replicas, NT, smem, stream>>>(p, K, cfg);
+    philox_kernel<NT, MINB, NearT, PPC><<<p.n_replicas, NT, smem, stream>>>(p, K, cfg);
     return cudaGetLastError();
 }
 
@@ -939,21 +957,19 @@ cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_
     uint32_t k0 = (uint32_t)s, k1 = (uint32_t)(s >> 32);
     for (int r = 0; r < 10; r++) { K.k[2 * r] = k0; K.k[2 * r + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
     // MINB caps the register count at 64 per thread (32 resident warps per SM when smem allows)
-#define MCL_CASE(NT_, MINB_)                                                                       \
+#define MCL_CASE(NT_, MINB_, PPC_)                                                                  \
     case NT_:                                                                                      \
-        return pl.near16 ? launch_one<NT_, MINB_, uint16_t>(p, K, cfg, pl.smem, stream)            \
-                         : launch_one<NT_, MINB_, uint32_t>(p, K, cfg, pl.smem, stream)
+        return pl.near16 ? launch_one<NT_, MINB_, uint16_t, PPC_>(p, K, cfg, pl.smem, stream)      \
+                         : launch_one<NT_, MINB_, uint32_t, PPC_>(p, K, cfg, pl.smem, stream)
     switch (pl.nt) {
-        MCL_CASE(32, 32);
-        MCL_CASE(64, 16);
-        MCL_CASE(128, 8);
-        MCL_CASE(256, 3);
-        MCL_CASE(320, 3);
-        MCL_CASE(384, 3);
+        MCL_CASE(32, 32, 1);
+        MCL_CASE(64, 16, 1);
+        MCL_CASE(128, 8, 1);
+        MCL_CASE(256, 3, 2);
         default: break;
     }
-    return pl.near16 ? launch_one<512, 2, uint16_t>(p, K, cfg, pl.smem, stream)
-                     : launch_one<512, 2, uint32_t>(p, K, cfg, pl.smem, stream);
+    return pl.near16 ? launch_one<512, 2, uint16_t, 2>(p, K, cfg, pl.smem, stream)
+                     : launch_one<512, 2, uint32_t, 2>(p, K, cfg, pl.smem, stream);
 #undef MCL_CASE
 }
 
