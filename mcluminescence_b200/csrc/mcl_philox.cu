@@ -683,6 +683,10 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 }
                 if (tid == 0) {
                     hpos[h].x = DEAD_X;
+                    // Bit h is the only bit of the bitmap that changes in this phase, and every concurrent reader
+                    // (retarget below, other warps) skips hole h before it looks at a word: reading the old or the
+                    // new word gives the same answer.  compute-sanitizer racecheck flags exactly this read / RMW
+                    // overlap; it is benign by construction.  The next barrier publishes the bit.
                     if (h < n_h0) hole_bm[h >> 5] &= ~(1u << (h & 31));
                     if (hist_on && p.hist_events) {
                         // edges up to t_cur have been passed: the event sits in the bin before the cursor
