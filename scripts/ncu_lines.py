@@ -8,7 +8,10 @@ rows = list(csv.reader(io.StringIO(out)))
 hdr = None
 lines = {}
 cur = None
+cur_file = ""
 for r in rows:
+    if r and r[0] == "File Path":
+        cur_file = (r[1] if len(r) > 1 else "").split("/")[-1]; continue
     if r and r[0] == "Line No":
         hdr = r
         isamp, iex, ithr = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
@@ -16,7 +19,7 @@ for r in rows:
     if hdr is None or len(r) < len(hdr):
         continue
     if r[0] != "":          # a CUDA source line header row (aggregated)
-        cur = (int(r[0]), r[1].strip())
+        cur = (int(r[0]), (cur_file + ": " if not cur_file.endswith("mcl_philox.cu") else "") + r[1].strip())
         try:
             lines[cur] = [int(r[isamp] or 0), int(r[iex] or 0), int(r[ithr] or 0)]
         except ValueError:

@@ -4,7 +4,7 @@ rep = sys.argv[1]
 src = open("mcluminescence_b200/csrc/mcl_philox.cu").read().split("\n")
 # region boundaries: lines that start a region (first match wins, in file order)
 marks = [("helpers/philox", r"^constexpr uint32_t PHILOX_M0"), ("warp searches", r"^struct Holes"),
-         ("kernel setup", r"^template <int NT, int MINB, typename NearT>"), ("seed holes", r"Box.seed \(engine.py:124-129\): holes"),
+         ("kernel setup", r"^template <int NT, int MINB, typename NearT, int PPC>"), ("seed holes", r"Box.seed \(engine.py:124-129\): holes"),
          ("seed electrons + sort", r"electrons, stored in grid-cell order"), ("K-nearest init", r"Box._rebuild \(engine.py:113-119\)"),
          ("leg setup", r"per-replica constants of the rate law"), ("step top", r"// ---------------- loop condition"),
          ("sweep", r"per-electron clocks \+ running argmin"), ("reduce+B1", r"// warp argmin -> one row per warp"),
@@ -20,8 +20,10 @@ for name, pat in marks:
 starts.sort()
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr = None; agg = {}
+hdr = None; agg = {}; cur_file = ""
 for r in rows:
+    if r and r[0] == "File Path":
+        cur_file = r[1] if len(r) > 1 else ""; continue
     if r and r[0] == "Line No":
         hdr = r; isamp, iex = hdr.index("# Samples"), hdr.index("Instructions Executed"); continue
     if hdr is None or len(r) < len(hdr) or r[0] == "":
@@ -30,10 +32,13 @@ for r in rows:
         ln, s_, i_ = int(r[0]), int(r[isamp] or 0), int(r[iex] or 0)
     except ValueError:
         continue
+    if not cur_file.endswith("mcl_philox.cu"):
+        a = agg.setdefault("(cuda headers: sync/shuffle/atomics)", [0, 0]); a[0] += s_; a[1] += i_
+        continue
     name = "before"
     for st, nm in starts:
         if ln >= st: name = nm
     a = agg.setdefault(name, [0, 0]); a[0] += s_; a[1] += i_
 ts = sum(a[0] for a in agg.values()); ti = sum(a[1] for a in agg.values())
-for st, nm in [(0, "before")] + starts:
+for st, nm in [(0, "before")] + starts + [(0, "(cuda headers: sync/shuffle/atomics)")]:
     if nm in agg: print(f"{nm:24s} inst {100*agg[nm][1]/ti:5.1f}%   samples {100*agg[nm][0]/ts:5.1f}%")

@@ -87,3 +87,16 @@ def test_replay_stream_is_numpys_legacy_stream_with_a_cursor():
     assert np.array_equal(st.window(2_000_000), ref[586:2_000_586])
     st.advance(3_000_000)
     assert np.array_equal(st.window(10), ref[3_000_586:3_000_596])
+
+
+def test_glow_curve_smoothing_matches_reference_definition():
+    from mcluminescence_b200.postprocess import decay_curve, glow_curve, running_mean
+    rs = np.random.RandomState(0)
+    hist = rs.poisson(20, size=300)
+    g = glow_curve(hist, n_replicas=10, bin_width=1.0, win_deg=50.0)
+    assert g.shape == (251,)
+    assert np.allclose(g[0], hist[:50].mean() / 10)
+    assert np.allclose(running_mean(np.arange(10.0), 5), np.arange(2.0, 8.0))
+    occ = np.array([40, 20]); occ2 = np.array([40 * 40 // 4 * 1 + 0, 120])   # 4 replicas
+    m, s = decay_curve(occ, np.array([400, 120]), 4, 10.0)
+    assert np.allclose(m, [1.0, 0.5]) and np.allclose(s, [0.0, np.sqrt(120 / 4 - 25) / 10])
