@@ -150,3 +150,42 @@ def test_objective_statistics_match_oracle(gpu, capsys):
     se = np.sqrt(g.var(ddof=1) / M + o.var(ddof=1) / M)
     assert abs(g.mean() - o.mean()) <= 4 * se, (g.mean(), o.mean(), se)
     capsys.readouterr()
+
+
+@pytest.mark.parametrize("which", ["c2", "c5"])
+def test_full_size_replicas_conserve_charge(gpu, which):
+    """BASELINE-sized replicas (10^4 / 2000 electrons): size-independent invariants of the kernel's own
+    outputs -- every recombination removes exactly one electron, histograms account for every event inside
+    the axis, occupancy is non-increasing without a dose, and the count is independent of the launch shape."""
+    from mcluminescence_b200 import engine, workloads
+    wl = workloads.c2(n_replicas=24) if which == "c2" else workloads.c5(n_replicas=96)
+    out = engine.run_replicas(wl["replicas"], wl["segments"], wl["max_steps"], seed=17, hist=wl["hist"],
+                              trace=True, sync=True)
+    out.raise_on_error()
+    n0 = wl["replicas"]["n_e0"].astype(np.int64)
+    events = np.array([out.event[r, :out.steps_used[r]].sum() for r in range(len(n0))])
+    assert np.array_equal(events + out.final_n_e, n0)                   # charge conservation, no fills
+    for r in range(0, len(n0), 7):
+        n = out.steps_used[r]
+        ne = out.n_e[r, :n]
+        assert np.all(np.diff(ne) <= 0) and np.all(np.diff(ne) >= -1)
+        assert np.all(np.diff(out.t[r, :n]) >= 0)
+        assert np.array_equal(np.concatenate([[n0[r]], ne[:-1]]) - ne, out.event[r, :n])
+    assert int(out.hist_events.sum()) <= int(events.sum())
+    assert int(out.esteps.sum()) == int(sum((out.n_e[r, :out.steps_used[r]] + out.event[r, :out.steps_used[r]]).sum()
+                                            for r in range(len(n0))))
+    # occupancy histogram is a sum of non-increasing step functions
+    occ = out.hist_occ
+    for row in range(occ.shape[0]):
+        nz = occ[row][occ[row] > 0]
+        assert np.all(np.diff(nz) <= 0)
+    # same replicas, forced onto a different CTA width: identical traces
+    import os
+    from mcluminescence_b200 import _native
+    os.environ["MCL_PHILOX_NT"] = "128" if which == "c2" else "32"
+    try:
+        alt = engine.run_replicas(wl["replicas"][:6], wl["segments"], wl["max_steps"], seed=17, trace=True, sync=True)
+    finally:
+        del os.environ["MCL_PHILOX_NT"]
+    assert np.array_equal(alt.event, out.event[:6]) and np.array_equal(alt.n_e, out.n_e[:6])
+    assert np.array_equal(alt.t, out.t[:6])
