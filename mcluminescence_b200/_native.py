@@ -74,7 +74,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    path = os.environ.get("MCL_B200_LIB", _build.LIB_PATH)      # override: A/B builds while tuning
     if not os.path.isfile(path):
         try:
             _build.build()
