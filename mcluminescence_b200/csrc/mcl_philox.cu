@@ -209,6 +209,125 @@ template <typename NearT> struct NearTraits;
 template <> struct NearTraits<uint16_t> { static constexpr uint32_t DEAD = 0xffffu; static constexpr int PER_VEC = 8; };
 template <> struct NearTraits<uint32_t> { static constexpr uint32_t DEAD = 0xffffffffu; static constexpr int PER_VEC = 4; };
 
+// Seeding, part 3 (Box._rebuild, engine.py:113-119): the KC nearest holes of every electron.
+// One warp per occupied cell: lanes 0..26 read the hole ranges of the 27 surrounding cells, the
+// (<= 128) holes are spread 4 per lane and loaded once, then each electron of the cell needs 4
+// distance evaluations per lane and KC warp-min rounds.
+template <typename NearT>
+__device__ __forceinline__ void seed_candidate_lists_impl(const Holes &H, const int *e_start, const float *ex, const float *ey,
+                                                          const float *ez, float4 *cand_d, NearT *cand_j, float *cr, NearT *near,
+                                                          int n_cells, int warp, int lane, int NW)
+{
+    constexpr uint32_t NEAR_DEAD = NearTraits<NearT>::DEAD;
+    const float4 *hpos = H.pos;
+    const int *cell_start = H.cell_start;
+    // all lanes hold the same (d2, slot) list; lane k < KC writes entry k
+    auto store_lists = [&](int i, const float d2[KC], const int jj[KC]) {
+        float myd = F_INF; int myj = -1;
+#pragma unroll
+        for (int k = 0; k < KC; k++) if (lane == k) { myd = d2[k]; myj = jj[k]; }
+        float d;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(myd));
+        if (myj < 0) d = F_INF;
+        if (lane < KC) {
+            reinterpret_cast<float *>(cand_d + i)[lane] = d;
+            cand_j[(size_t)i * KC + lane] = myj >= 0 ? (NearT)myj : (NearT)NEAR_DEAD;
+            if (lane == 0) { cr[i] = d; near[i] = myj >= 0 ? (NearT)myj : (NearT)NEAR_DEAD; }
+        }
+    };
+    auto slow_lists = [&](int i) {            // generic ring search (crowded cell or a list that is not yet exact)
+        unsigned long long b[KC];
+        warp_nearest_k(H, ex[i], ey[i], ez[i], lane, b);
+        float d2[KC]; int jj[KC];
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+            const bool ok = b[k] != ~0ull;
+            d2[k] = ok ? __uint_as_float((uint32_t)(b[k] >> 32)) : F_INF;
+            jj[k] = ok ? (int)(uint32_t)b[k] : -1;
+        }
+        store_lists(i, d2, jj);
+    };
+    const int G = H.G;
+    for (int c = warp; c < n_cells; c += NW) {
+        const int i0 = e_start[c], i1 = e_start[c + 1];
+        if (i0 == i1) continue;                                     // warp-uniform
+        const int ax = c / (G * G), ay = (c / G) % G, az = c % G;
+        const int nx_ = ax + lane / 9 - 1, ny_ = ay + (lane / 3) % 3 - 1, nz_ = az + lane % 3 - 1;
+        const bool valid = lane < 27 && (unsigned)nx_ < (unsigned)G && (unsigned)ny_ < (unsigned)G && (unsigned)nz_ < (unsigned)G;
+        const int nc = valid ? (nx_ * G + ny_) * G + nz_ : 0;
+        const int j0 = valid ? cell_start[nc] : 0;
+        const int cnt = valid ? cell_start[nc + 1] - j0 : 0;
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        const int off = inc - cnt;
+        if (total > 128) { for (int i = i0; i < i1; i++) slow_lists(i); continue; }
+        float4 hp[4]; int hj[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int item = lane + 32 * k;
+            int pos = 0;                                            // last lane whose range starts at or before item
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                const int t = __shfl_sync(0xffffffffu, off, min(pos + sft, 31));
+                if (pos + sft < 32 && t <= item) pos += sft;
+            }
+            const int jbase = __shfl_sync(0xffffffffu, j0, pos), obase = __shfl_sync(0xffffffffu, off, pos);
+            const bool on = item < total;
+            hj[k] = on ? jbase + (item - obase) : -1;
+            hp[k] = on ? hpos[hj[k]] : make_float4(DEAD_X, 0.f, 0.f, 0.f);
+        }
+        // everything outside the 3x3x3 block is at least this far from an electron of cell c
+        const float lo_x = (ax > 0) ? (ax - 1) * H.w : -F_INF, hi_x = (ax < G - 1) ? (ax + 2) * H.w : F_INF;
+        const float lo_y = (ay > 0) ? (ay - 1) * H.w : -F_INF, hi_y = (ay < G - 1) ? (ay + 2) * H.w : F_INF;
+        const float lo_z = (az > 0) ? (az - 1) * H.w : -F_INF, hi_z = (az < G - 1) ? (az + 2) * H.w : F_INF;
+        for (int i = i0; i < i1; i++) {
+            const float x = ex[i], y = ey[i], z = ez[i];
+            float d2[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float dx = x - hp[k].x, dy = y - hp[k].y, dz = z - hp[k].z;
+                d2[k] = fmaf(dx, dx, fmaf(dy, dy, dz * dz));                   // inf for an unused register
+            }
+            float od[KC]; int oj[KC];
+#pragma unroll
+            for (int r_ = 0; r_ < KC; r_++) {
+                const float m = fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3]));
+                const float g_ = warp_min_f32(m);
+                const unsigned who = __ballot_sync(0xffffffffu, m == g_);
+                const int owner = who ? __ffs(who) - 1 : 0;
+                // branch-free: every lane picks its own best register; only the owner retires it
+                int ksel = 3;
+#pragma unroll
+                for (int k = 2; k >= 0; k--) if (d2[k] == m) ksel = k;
+                int mine_j = hj[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) if (k == ksel) mine_j = hj[k];
+                const bool retire = (lane == owner);
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (retire && k == ksel) d2[k] = F_INF;
+                oj[r_] = (g_ < F_INF) ? __shfl_sync(0xffffffffu, mine_j, owner) : -1;
+                od[r_] = g_;
+            }
+            // a face of the block that lies inside the grid limits how far the list is provably complete
+            const float bound = fminf(fminf(fminf(x - lo_x, hi_x - x), fminf(y - lo_y, hi_y - y)), fminf(z - lo_z, hi_z - z));
+            if (od[KC - 1] <= bound * bound) store_lists(i, od, oj);
+            else slow_lists(i);
+        }
+    }
+}
+
+// Out of line for the wide CTAs (keeps its register needs away from the allocation of their step loop),
+// inline for the narrow ones (where the call ABI costs more than it saves).
+template <typename NearT>
+__device__ __noinline__ void seed_candidate_lists_call(const Holes &H, const int *e_start, const float *ex, const float *ey,
+                                                       const float *ez, float4 *cand_d, NearT *cand_j, float *cr, NearT *near,
+                                                       int n_cells, int warp, int lane, int NW)
+{
+    seed_candidate_lists_impl<NearT>(H, e_start, ex, ey, ez, cand_d, cand_j, cr, near, n_cells, warp, lane, NW);
+}
+
 template <int NT, int MINB, typename NearT, int PPC>
 __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, const RoundKeys K, const Cfg cfg)
 {
@@ -369,99 +488,10 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             ex[i] = x; ey[i] = y; ez[i] = z;
         }
         cta_sync<NT>();
-        // ---------------- Box._rebuild (engine.py:113-119): the KC nearest holes of every electron.
-        // One warp per occupied cell: lanes 0..26 read the hole ranges of the 27 surrounding cells, the
-        // (<= 128) holes are spread 4 per lane and loaded once, then each electron of the cell needs 4
-        // distance evaluations per lane and KC warp-min rounds.
-        auto store_lists = [&](int i, const float d2[KC], const int jj[KC]) {      // lane 0
-            float d[KC];
-#pragma unroll
-            for (int k = 0; k < KC; k++) {
-                d[k] = jj[k] >= 0 ? sqrtf(d2[k]) : F_INF;
-                cand_j[(size_t)i * KC + k] = jj[k] >= 0 ? (NearT)jj[k] : (NearT)NEAR_DEAD;
-            }
-            cand_d[i] = make_float4(d[0], d[1], d[2], d[3]);
-            cr[i] = d[0]; near[i] = jj[0] >= 0 ? (NearT)jj[0] : (NearT)NEAR_DEAD;
-        };
-        auto slow_lists = [&](int i) {            // generic ring search (crowded cell or a list that is not yet exact)
-            unsigned long long b[KC];
-            warp_nearest_k(H, ex[i], ey[i], ez[i], lane, b);
-            float d2[KC]; int jj[KC];
-#pragma unroll
-            for (int k = 0; k < KC; k++) {
-                const bool ok = b[k] != ~0ull;
-                d2[k] = ok ? __uint_as_float((uint32_t)(b[k] >> 32)) : F_INF;
-                jj[k] = ok ? (int)(uint32_t)b[k] : -1;
-            }
-            if (lane == 0) store_lists(i, d2, jj);
-        };
-        const int G = H.G;
-        for (int c = warp; c < n_cells; c += NW) {
-            const int i0 = e_start[c], i1 = e_start[c + 1];
-            if (i0 == i1) continue;                                     // warp-uniform
-            const int ax = c / (G * G), ay = (c / G) % G, az = c % G;
-            const int nx_ = ax + lane / 9 - 1, ny_ = ay + (lane / 3) % 3 - 1, nz_ = az + lane % 3 - 1;
-            const bool valid = lane < 27 && (unsigned)nx_ < (unsigned)G && (unsigned)ny_ < (unsigned)G && (unsigned)nz_ < (unsigned)G;
-            const int nc = valid ? (nx_ * G + ny_) * G + nz_ : 0;
-            const int j0 = valid ? cell_start[nc] : 0;
-            const int cnt = valid ? cell_start[nc + 1] - j0 : 0;
-            int inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            const int total = __shfl_sync(0xffffffffu, inc, 31);
-            const int off = inc - cnt;
-            if (total > 128) { for (int i = i0; i < i1; i++) slow_lists(i); continue; }
-            float4 hp[4]; int hj[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int item = lane + 32 * k;
-                int pos = 0;                                            // last lane whose range starts at or before item
-#pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) {
-                    const int t = __shfl_sync(0xffffffffu, off, min(pos + sft, 31));
-                    if (pos + sft < 32 && t <= item) pos += sft;
-                }
-                const int jbase = __shfl_sync(0xffffffffu, j0, pos), obase = __shfl_sync(0xffffffffu, off, pos);
-                const bool on = item < total;
-                hj[k] = on ? jbase + (item - obase) : -1;
-                hp[k] = on ? hpos[hj[k]] : make_float4(DEAD_X, 0.f, 0.f, 0.f);
-            }
-            // everything outside the 3x3x3 block is at least this far from an electron of cell c
-            const float lo_x = (ax > 0) ? (ax - 1) * H.w : -F_INF, hi_x = (ax < G - 1) ? (ax + 2) * H.w : F_INF;
-            const float lo_y = (ay > 0) ? (ay - 1) * H.w : -F_INF, hi_y = (ay < G - 1) ? (ay + 2) * H.w : F_INF;
-            const float lo_z = (az > 0) ? (az - 1) * H.w : -F_INF, hi_z = (az < G - 1) ? (az + 2) * H.w : F_INF;
-            for (int i = i0; i < i1; i++) {
-                const float x = ex[i], y = ey[i], z = ez[i];
-                float d2[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float dx = x - hp[k].x, dy = y - hp[k].y, dz = z - hp[k].z;
-                    d2[k] = fmaf(dx, dx, fmaf(dy, dy, dz * dz));                   // inf for an unused register
-                }
-                float od[KC]; int oj[KC];
-#pragma unroll
-                for (int r_ = 0; r_ < KC; r_++) {
-                    const float m = fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3]));
-                    const float g_ = warp_min_f32(m);
-                    const unsigned who = __ballot_sync(0xffffffffu, m == g_);
-                    const int owner = who ? __ffs(who) - 1 : 0;
-                    int mine_j = -1;
-                    if (lane == owner) {
-                        int ksel = -1;
-#pragma unroll
-                        for (int k = 3; k >= 0; k--) if (d2[k] == m) ksel = k;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) if (k == ksel) { mine_j = hj[k]; d2[k] = F_INF; }
-                    }
-                    oj[r_] = (g_ < F_INF) ? __shfl_sync(0xffffffffu, mine_j, owner) : -1;
-                    od[r_] = g_;
-                }
-                // a face of the block that lies inside the grid limits how far the list is provably complete
-                const float bound = fminf(fminf(fminf(x - lo_x, hi_x - x), fminf(y - lo_y, hi_y - y)), fminf(z - lo_z, hi_z - z));
-                if (od[KC - 1] <= bound * bound) { if (lane == 0) store_lists(i, od, oj); }
-                else slow_lists(i);
-            }
-        }
+        // ---------------- Box._rebuild (engine.py:113-119): the KC nearest holes of every electron (kept out of
+        // line so that its register needs do not disturb the allocation of the step loop)
+        if (NT >= 256) seed_candidate_lists_call<NearT>(H, cell_fill, ex, ey, ez, cand_d, cand_j, cr, near, n_cells, warp, lane, NW);
+        else seed_candidate_lists_impl<NearT>(H, cell_fill, ex, ey, ez, cand_d, cand_j, cr, near, n_cells, warp, lane, NW);
         cta_sync<NT>();
     }
 
@@ -961,10 +991,14 @@ cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_
     uint32_t k0 = (uint32_t)s, k1 = (uint32_t)(s >> 32);
     for (int r = 0; r < 10; r++) { K.k[2 * r] = k0; K.k[2 * r + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
     // MINB caps the register count at 64 per thread (32 resident warps per SM when smem allows)
+#define MCL_GO(NT_, MINB_, PPC_)                                                                    \
+    (pl.near16 ? launch_one<NT_, MINB_, uint16_t, PPC_>(p, K, cfg, pl.smem, stream)                \
+               : launch_one<NT_, MINB_, uint32_t, PPC_>(p, K, cfg, pl.smem, stream))
 #define MCL_CASE(NT_, MINB_, PPC_)                                                                  \
     case NT_:                                                                                      \
-        return pl.near16 ? launch_one<NT_, MINB_, uint16_t, PPC_>(p, K, cfg, pl.smem, stream)      \
-                         : launch_one<NT_, MINB_, uint32_t, PPC_>(p, K, cfg, pl.smem, stream)
+        return (ppc_override ? ppc_override : PPC_) == 2 ? MCL_GO(NT_, MINB_, 2) : MCL_GO(NT_, MINB_, 1)
+    int ppc_override = 0;
+    if (const char *env = getenv("MCL_PHILOX_PPC")) { int v = atoi(env); if (v == 1 || v == 2) ppc_override = v; }   // tuning knob
     switch (pl.nt) {
         MCL_CASE(32, 32, 1);
         MCL_CASE(64, 16, 1);
@@ -972,8 +1006,8 @@ cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_
         MCL_CASE(256, 3, 2);
         default: break;
     }
-    return pl.near16 ? launch_one<512, 2, uint16_t, 2>(p, K, cfg, pl.smem, stream)
-                     : launch_one<512, 2, uint32_t, 2>(p, K, cfg, pl.smem, stream);
+    return (ppc_override ? ppc_override : 2) == 2 ? MCL_GO(512, 2, 2) : MCL_GO(512, 2, 1);
+#undef MCL_GO
 #undef MCL_CASE
 }
 
