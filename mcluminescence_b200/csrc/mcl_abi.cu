@@ -32,7 +32,7 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
     if (a->max_steps <= 0) { set_error("mcl_run: max_steps must be positive"); return MCL_ERR_ARG; }
     if (a->mode != MCL_MODE_PHILOX && a->mode != MCL_MODE_REPLAY) { set_error("mcl_run: unknown mode %d", a->mode); return MCL_ERR_ARG; }
     int ne_max = 0, nh_max = 0, seg_max = 1;
-    bool any_dose = false, any_lab = false;
+    bool any_dose = false;
     for (int r = 0; r < a->n_replicas; r++) {
         const mcl_replica &rp = a->replicas[r];
         if (rp.N_e < 0 || rp.n_e0 < 0 || rp.n_h0 < 0) { set_error("replica %d: negative sizes", r); return MCL_ERR_ARG; }
@@ -47,10 +47,8 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
         ne_max = std::max(ne_max, std::max(rp.N_e, rp.n_e0));
         nh_max = std::max(nh_max, rp.n_h0);
         seg_max = std::max(seg_max, rp.seg_count);
-        if (rp.protocol != MCL_PROTO_SIMULATE) any_lab = true;
         for (int s = 0; s < rp.seg_count; s++) if (a->segments[rp.seg_begin + s].dose_rate != 0.0) any_dose = true;
     }
-    (void)any_lab;
     L->cap_e = ne_max + 8 + seg_max;
     if (a->mode == MCL_MODE_REPLAY) L->cap_h = nh_max + L->cap_e + 8;
     else L->cap_h = nh_max + (any_dose ? nh_max + ne_max : 0) + 64 + seg_max;

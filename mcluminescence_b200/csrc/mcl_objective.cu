@@ -7,12 +7,9 @@
 // Geometry is derived with the reference's own expressions in C doubles (Python's float `**` is
 // C pow), so int() truncations agree with the Python host path.
 #include <cmath>
+#include <cstring>
 #include <vector>
 #include "mcl_common.cuh"
-
-namespace mcl {
-int run_device_args(const mcl_run_args *a);      // mcl_abi.cu
-}
 
 namespace {
 

@@ -1,27 +1,35 @@
 // mcl_philox.cu -- native throughput kernel of the trapped-charge kinetics loop (sm_100a).
 //
-// One CTA (NT = 32..512 threads) per replica; one electron per smem slot, two slots per Philox
-// call.  What one step does (reference src/class/simulate.py:51-92, tl_trap_lab.py:90-108):
-//   1. every alive electron i draws a selector and an exponential and forms its waiting time
+// One CTA (NT = 32..512 threads) per replica; one electron per shared-memory slot, two slots per
+// Philox call.  What one step does (reference src/class/simulate.py:51-92, tl_trap_lab.py:90-108):
+//   1. SWEEP.  Every alive electron i draws a selector and an exponential and forms its waiting time
 //        wait_i = E_i / (k_cb + b*exp(-E_loc/kT - alpha*r_i))          (engine.py:65-77, tl_trap_lab.py:51)
 //      in the log2 domain:  l_i = lg2(-lg2 u_i) - lg2 k_i,  wait_i = ln2 * 2^l_i,
 //      so neither the tunnelling factor (alpha*r up to several hundred) nor E_cb/kT can under/overflow
-//      FP32.  SFU ops per electron-step: lg2, lg2 (+ ex2, lg2 when the conduction-band rate matters);
-//   2. CTA-wide argmin: per-thread running min -> CREDUX.MIN.F32 + ballot per warp -> one smem
-//      row per warp -> ONE __syncthreads -> every warp re-reduces the <=16 rows (double-buffered);
-//   3. dt = min(dt_fill, dt_recomb, dt_cap); fill -> add electron+hole (stale cache semantics of
-//      engine.py:133-152), recombination -> remove the pair and re-search the electrons that
-//      pointed at the dead hole (engine.py:154-175) through a uniform cell grid over the holes;
-//   4. the (event, n_e, t) record is staged in smem and flushed 32 steps at a time with coalesced
-//      stores; optional fused integer histograms of events / occupancy replace the trace for
-//      large ensembles.
+//      FP32.  SFU ops per electron-step: lg2, lg2 (+ ex2, lg2 when the conduction-band rate matters).
+//      A thread owns whole chunks of slots (chunk b -> thread b % NT); outside barrier-protected phases
+//      only the owner touches cr[] / near[] of its slots.
+//   2. ARGMIN.  Per-thread running min -> CREDUX.MIN.F32 + ballot per warp -> one smem row per warp
+//      (value, slot, its hole), double-buffered by step parity -> ONE __syncthreads -> every warp
+//      re-reduces the <= 16 rows and derives the same decision from uniform inputs.
+//   3. EVENT.  dt = min(dt_fill, dt_recomb, dt_cap).  Recombination (engine.py:154-175): the owner
+//      tombstones the slot; every thread scans the near[] entries of its own chunks for the dead hole; a hit
+//      is re-targeted by its owner from the electron's K nearest-hole candidate list (exact while no hole
+//      was ever added), else by a grid search of the owner's warp.  No CTA barrier.  Fill
+//      (engine.py:133-152, stale-cache semantics): warp 0 places the pair; one extra barrier.
+//   4. OUTPUT.  The (event, n_e, t) record is staged in smem and flushed 32 steps at a time with
+//      coalesced stores; fused integer histograms of events / occupancy replace the trace for ensembles.
+// Seeding (Box.seed/_rebuild, engine.py:113-129): holes and electrons are counting-sorted into a uniform
+// cell grid; one warp per occupied cell loads the ~95 surrounding holes into registers once and builds the
+// K-nearest lists of the cell's electrons.
 // Random numbers: Philox4x32-10, key = seed (launch-wide round keys live in the constant bank),
 // counter = (slot pair | element index, step, replica id lo, replica id hi | domain).  Results
 // depend only on (seed, global replica id), never on the launch shape or the GPU count.
 //
-// Electron state: cr[slot] = alpha*log2(e)*r (FP32, +inf = empty slot), near[slot] = hole slot, both
-// in shared memory; coordinates (pre-scaled by alpha*log2 e) in the replica's HBM slab and only
-// touched on events.  Holes: [0,n_h0) sorted by grid cell (+cell_start table), [n_h0, ...) fills.
+// Electron state: cr[slot] = alpha*log2(e)*r (FP32, +inf = empty slot), near[slot] = hole slot, both in
+// shared memory, plus a 1-bit-per-hole alive bitmap; coordinates (pre-scaled by alpha*log2 e) and candidate
+// lists in the replica's HBM slab, touched only on events.  Holes: [0,n_h0) sorted by grid cell
+// (+cell_start table), [n_h0, ...) added by fills.
 #include <math_constants.h>
 #include <type_traits>
 #include <cstdlib>
@@ -206,8 +214,8 @@ __device__ __forceinline__ void cta_sync()
 // hole capacity allows (halves the footprint and the traffic of the post-event scan); the all-ones
 // value marks an empty electron slot.
 template <typename NearT> struct NearTraits;
-template <> struct NearTraits<uint16_t> { static constexpr uint32_t DEAD = 0xffffu; static constexpr int PER_VEC = 8; };
-template <> struct NearTraits<uint32_t> { static constexpr uint32_t DEAD = 0xffffffffu; static constexpr int PER_VEC = 4; };
+template <> struct NearTraits<uint16_t> { static constexpr uint32_t DEAD = 0xffffu; };
+template <> struct NearTraits<uint32_t> { static constexpr uint32_t DEAD = 0xffffffffu; };
 
 // Seeding, part 3 (Box._rebuild, engine.py:113-119): the KC nearest holes of every electron.
 // One warp per occupied cell: lanes 0..26 read the hole ranges of the 27 surrounding cells, the
@@ -351,7 +359,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     __shared__ uint32_t stepdraw[2][4];
     __shared__ int rec_ev[32], rec_ne[32];
     __shared__ double rec_t[32];
-    __shared__ int s_nflag, s_scan[33];
+    __shared__ int s_scan[33];
 
     // ---------------- HBM slab
     unsigned char *ws = p.ws + (size_t)r * p.ws_stride;
@@ -360,7 +368,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     float4 *hpos = reinterpret_cast<float4 *>(ws + cfg.off_holes);    // [cap_h] (x, y, z, original index)
     int *cell_start = reinterpret_cast<int *>(hpos + ch);             // [cap_cells]
     int *cell_fill = cell_start + cfg.cap_cells;                      // [cap_cells] init only
-    int *flist = cell_fill + cfg.cap_cells;                           // [cap_e]
+    int *e_id_buf = cell_fill + cfg.cap_cells;                        // [cap_e] seeding only
     float4 *cand_d = reinterpret_cast<float4 *>(ws + cfg.off_cand);   // [cap_e] cr of the KC nearest initial holes
     NearT *cand_j = reinterpret_cast<NearT *>(cand_d + ce);           // [cap_e][KC] their slots (NEAR_DEAD = none)
 
@@ -380,7 +388,6 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
 
     for (int s = tid; s < cfg.cap_slots; s += NT) { cr[s] = F_INF; near[s] = (NearT)NEAR_DEAD; }
     for (int w = tid; w < cfg.bm_words; w += NT) hole_bm[w] = 0xffffffffu;
-    if (tid == 0) s_nflag = 0;
 
     if (status == MCL_OK) {
         // ---------------- Box.seed (engine.py:124-129): holes, binned into the cell grid
@@ -444,7 +451,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             x = u01(c0) * core_s; y = u01(c1) * core_s; z = u01(c2) * core_s;
         };
         int *e_start = cell_fill;                 // per-cell electron counts -> exclusive starts
-        int *e_id = flist;                        // original electron index held by every sorted slot
+        int *e_id = e_id_buf;                     // original electron index held by every sorted slot
         for (int c = tid; c <= n_cells; c += NT) e_start[c] = 0;
         for (int i = tid; i < n_e; i += NT) e_id[i] = -1;
         cta_sync<NT>();
