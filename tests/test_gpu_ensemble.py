@@ -189,3 +189,37 @@ def test_full_size_replicas_conserve_charge(gpu, which):
         del os.environ["MCL_PHILOX_NT"]
     assert np.array_equal(alt.event, out.event[:6]) and np.array_equal(alt.n_e, out.n_e[:6])
     assert np.array_equal(alt.t, out.t[:6])
+
+
+def test_objective_statistics_across_the_parameter_bounds(gpu, capsys):
+    """Sobol candidates spanning DEFAULT_BOUNDS (alpha up to 5e10, rho' down to 1e-8, E_cb ~2 eV: the
+    regimes where alpha*r is in the hundreds and the conduction-band channel dominates): the mean final
+    fill of every lab row, GPU Philox vs CPU oracle, over 48 independent evaluations per candidate."""
+    from mcluminescence_b200 import optimizer
+    from mcluminescence_b200.config import compose, initialize_runs
+    from mcluminescence_b200.optimizer import cfg_with_params
+    from mcluminescence_b200.replicas import LAB_CSV, LabTable
+    from mcluminescence_b200.workloads import c4_candidates
+    from oracle import mcl_oracle as mo
+    from mcluminescence_b200 import engine
+    cfg = compose(overrides=helpers.LAB_OVERRIDES)
+    P = c4_candidates(6, seed=11)
+    lt = LabTable(*LAB_CSV["tl_clbr"], helpers.DATA_ROOT)
+    M = 48
+    for c in range(P.shape[1]):
+        run = initialize_runs(cfg_with_params(cfg.deepcopy(), P[:, c]))[0]
+        reps1, segs = lt.tables(run)
+        reps = np.tile(reps1, M)
+        steps = int(run.exp_type_fp.steps)
+        out = engine.run_replicas(reps, segs, steps, seed=50 + c, trace=False, sync=True)
+        ref = mo.run(reps, segs, steps, seed=900 + c, parallel=True, trace=False)
+        if ref.rc != 0 or np.any(out.status != 0):
+            # a candidate the reference itself cannot finish within `steps`: both must agree on that
+            assert ref.rc != 0 and np.any(out.status != 0), (c, ref.rc, out.status[out.status != 0][:3])
+            continue
+        g = out.final_n_e.reshape(M, -1).astype(float)
+        o = ref.final_n_e.reshape(M, -1).astype(float)
+        for k in range(g.shape[1]):
+            se = np.sqrt(g[:, k].var(ddof=1) / M + o[:, k].var(ddof=1) / M)
+            assert abs(g[:, k].mean() - o[:, k].mean()) <= 4.5 * se + 0.35, (c, k, g[:, k].mean(), o[:, k].mean(), se)
+    capsys.readouterr()

@@ -144,3 +144,48 @@ def test_lab_protocol_ensemble_matches_oracle(gpu, exp):
         assert_means_agree(g[:, k], o[:, k], f"{exp}: column {k}")
     ge, oe = out.esteps.reshape(M, n_rows).sum(1).astype(float), ref.esteps.reshape(M, n_rows).sum(1).astype(float)
     assert_means_agree(ge, oe, f"{exp}: electron-steps per objective")
+
+
+def test_simulate_api_in_philox_mode(gpu, tmp_path):
+    """The public drop-in call with native random numbers: shapes, zero padding, CSV, reproducibility."""
+    from mcluminescence_b200 import simulate as sim_mod
+    from mcluminescence_b200.config import compose
+    cfg = compose(overrides=["exp_type_fp.N_e=300", "exp_type_fp.holes=300", "exp_type_fp.steps=3000",
+                             "exp_type_fp.T_rate=[5,20]", "exp_type_fp.duration=[120,40]", "exp_type_fp.sims=3",
+                             "+tag=philox", "+seed=42"])
+    sim_mod.PROJECT_ROOT = str(tmp_path)
+    x_ax, lum, er, configs = sim_mod.simulate(cfg)
+    assert x_ax.shape == lum.shape == er.shape == (3000, 3, 2) and len(configs) == 2
+    for run in range(2):
+        for j in range(3):
+            n = int(np.count_nonzero(x_ax[:, j, run] > 0))
+            assert 0 < n < 3000 and not x_ax[n:, j, run].any() and not lum[n:, j, run].any()
+            assert np.all(np.diff(x_ax[:n, j, run]) >= 0) and x_ax[n - 1, j, run] >= configs[run].exp_type_fp.duration
+            assert set(np.unique(lum[:n, j, run])) <= {0.0, 1.0}
+            ne = np.rint(er[:n, j, run] * 300)
+            assert np.array_equal(300 - np.cumsum(lum[:n, j, run]), ne)          # every event removes one electron
+    import pandas as pd
+    df = pd.read_csv(tmp_path / "results" / "simulations" / "exp_philox.csv")
+    assert list(df.columns) == ["run", "sim", "step", "lum", "electron_ratio"] and len(df) == 3000 * 3 * 2
+    again = sim_mod.simulate(cfg, write_csv=False)
+    assert np.array_equal(again[0], x_ax) and np.array_equal(again[1], lum)       # same seed -> same run
+    other = sim_mod.simulate(cfg, seed=43, write_csv=False)
+    assert not np.array_equal(other[1], lum)
+
+
+def test_tltrapsim_api_in_philox_mode(gpu, capsys):
+    from mcluminescence_b200.config import compose, initialize_runs
+    from mcluminescence_b200.tl_trap_lab import TLTrapSim
+    run = initialize_runs(compose(overrides=helpers.LAB_OVERRIDES))[0]
+    sim = TLTrapSim(run, seed=7)
+    a = sim.TL_lab("CLBR_IRSL50_0.25KperGy")
+    b = TLTrapSim(run, seed=7).TL_lab("CLBR_IRSL50_0.25KperGy")
+    c = TLTrapSim(run, seed=8).ISO_lab("CLBR_IR50_ISO")
+    assert a == b and 0.0 <= a < 1.0 and 0.0 <= c < 1.0 and sim.last_esteps > 0
+    out = capsys.readouterr().out
+    assert out.count("absError=") == 3 and "P_retrap=0.5" in out
+    with pytest.raises(FileNotFoundError):
+        TLTrapSim(run, seed=1).TL_lab("no_such_csv")
+    with pytest.raises(TypeError):
+        bad = initialize_runs(compose(overrides=["exp_type_fp=TLlab", "physics_fp=BG_basic"]))[0]
+        TLTrapSim(bad)
