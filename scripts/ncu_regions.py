@@ -5,7 +5,7 @@ src = open("mcluminescence_b200/csrc/mcl_philox.cu").read().split("\n")
 # region boundaries: lines that start a region (first match wins, in file order)
 marks = [("helpers/philox", r"^constexpr uint32_t PHILOX_M0"), ("warp searches", r"^struct Holes"),
          ("CTA barrier (cta_sync)", r"^__device__ __forceinline__ void cta_sync"), ("kernel setup", r"^template <int NT, int MINB, typename NearT, int PPC>"), ("seed holes", r"Box.seed \(engine.py:124-129\): holes"),
-         ("seed electrons + sort", r"electrons, stored in grid-cell order"), ("K-nearest init", r"Box._rebuild \(engine.py:113-119\)"),
+         ("seed electrons + sort", r"electrons, stored in grid-cell order"), ("K-nearest init", r"^// Seeding, part 3 \(Box._rebuild"), ("K-nearest init (call site)", r"Box._rebuild \(engine.py:113-119\): the KC nearest holes of every electron \(kept"),
          ("leg setup", r"per-replica constants of the rate law"), ("step top", r"// ---------------- loop condition"),
          ("sweep", r"per-electron clocks \+ running argmin"), ("reduce+B1", r"// warp argmin -> one row per warp"),
          ("scalar/dt", r"filling clock \(tl_trap_lab.py:53-60\) and dt"), ("histogram", r"fused occupancy histogram"),
