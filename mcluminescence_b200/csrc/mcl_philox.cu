@@ -950,7 +950,7 @@ struct PhiloxPlan { int nt; int cap_slots; int g_max; int cap_cells; int bm_word
 static int g_nt_override = 0;
 void philox_set_block_threads(int nt) { g_nt_override = nt; }
 
-static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override)
+static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override, int n_replicas = 1 << 30)
 {
     PhiloxPlan pl;
     pl.cap_slots = (int)align_up((size_t)cap_e + 2, 64);
@@ -963,11 +963,15 @@ static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override)
     size_t b = pl.off_holes + 16 * (size_t)cap_h + sizeof(int) * (2 * (size_t)pl.cap_cells + (size_t)cap_e);
     pl.off_cand = align_up(b, 16);
     pl.stride = align_up(pl.off_cand + (size_t)cap_e * (16 + 4 * (pl.near16 ? 2 : 4)), 256);
+    // CTA width: throughput optimum measured on B200 (2000 electrons: 64 threads, 10^4: 256).  Results do not
+    // depend on it.  With fewer replicas than SMs the launch is latency-bound: widen the CTAs instead.
     int nt;
     if (cap_e <= 256) nt = 32;
-    else if (cap_e <= 1024) nt = 64;
-    else if (cap_e <= 4096) nt = 128;
+    else if (cap_e <= 3072) nt = 64;
+    else if (cap_e <= 6144) nt = 128;
     else nt = 256;
+    if (n_replicas <= 148) nt = nt * 4 > 512 ? 512 : nt * 4;
+    else if (n_replicas <= 296) nt = nt * 2 > 512 ? 512 : nt * 2;
     if (const char *env = getenv("MCL_PHILOX_NT")) nt_override = atoi(env);     // tuning knob
     if (nt_override == 32 || nt_override == 64 || nt_override == 128 || nt_override == 256 || nt_override == 512)
         nt = nt_override;
@@ -991,7 +995,7 @@ static cudaError_t launch_one(const LaunchParams &p, const RoundKeys &K, const C
 
 cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_slots*/)
 {
-    PhiloxPlan pl = make_plan(p.cap_e, p.cap_h, g_nt_override);
+    PhiloxPlan pl = make_plan(p.cap_e, p.cap_h, g_nt_override, p.n_replicas);
     Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.off_holes, pl.off_cand};
     RoundKeys K;
     uint64_t s = mix64(p.seed);
