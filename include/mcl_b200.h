@@ -9,7 +9,7 @@
  * Conventions
  *   - plain C types only; every pointer is either HOST or DEVICE memory as marked;
  *   - caller owns every buffer; the library keeps no state between calls except the
- *     thread-local last-error string;
+ *     thread-local last-error string and mcl_objective's cached scratch slab (mcl_release_scratch);
  *   - return value: 0 on success, negative MCL_ERR_* otherwise (message via mcl_last_error());
  *   - calls enqueue on the CUDA stream in args->stream (0 = legacy default stream) and do not
  *     synchronise unless stated.
@@ -158,6 +158,8 @@ typedef struct mcl_lab {
 } mcl_lab;
 int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uint64_t seed,
                   uint64_t candidate_id0, double *mse, int64_t *esteps_total, void *stream);
+/* mcl_objective keeps its (multi-GB) device scratch between calls; this frees it. */
+void mcl_release_scratch(void);
 
 /* Issue-rate microbenchmarks for the roofline denominators (SFU, FP32 FMA, INT32 multiply-add,
  * LOP3), measured on the current device.  Results in giga lane-ops per second. */

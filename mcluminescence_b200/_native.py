@@ -14,7 +14,7 @@ ABI_VERSION = 1
 
 EXPORTS = (
     "mcl_abi_version", "mcl_last_error", "mcl_workspace_bytes", "mcl_run", "mcl_run_host",
-    "mcl_device_peaks", "mcl_objective",
+    "mcl_device_peaks", "mcl_objective", "mcl_release_scratch",
 )
 
 

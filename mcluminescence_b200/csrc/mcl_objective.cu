@@ -8,6 +8,7 @@
 // C pow), so int() truncations agree with the Python host path.
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <vector>
 #include "mcl_common.cuh"
 
@@ -36,6 +37,39 @@ struct DevBuf {
     ~DevBuf() { if (p) cudaFree(p); }
     bool alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess; }
 };
+
+// The scratch slab of an Optimizer population is gigabytes; allocating and freeing it on every call
+// costs anything from 1 ms to 0.5 s.  It is kept (grow-only, per device) between calls and handed back
+// by mcl_release_scratch().  This is the only state the library keeps.
+struct ScratchCache {
+    std::mutex mu;
+    void *ptr[64] = {nullptr};
+    size_t bytes[64] = {0};
+    void *get(size_t need)
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+        std::lock_guard<std::mutex> lk(mu);
+        if (bytes[dev] < need) {
+            if (ptr[dev]) cudaFree(ptr[dev]);
+            ptr[dev] = nullptr; bytes[dev] = 0;
+            size_t want = need + need / 8;
+            if (cudaMalloc(&ptr[dev], want) != cudaSuccess) {
+                cudaGetLastError();
+                if (cudaMalloc(&ptr[dev], need) != cudaSuccess) { ptr[dev] = nullptr; return nullptr; }
+                want = need;
+            }
+            bytes[dev] = want;
+        }
+        return ptr[dev];
+    }
+    void release()
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (int d = 0; d < 64; d++) if (ptr[d]) { cudaSetDevice(d); cudaFree(ptr[d]); ptr[d] = nullptr; bytes[d] = 0; }
+    }
+};
+ScratchCache g_scratch;
 
 }  // namespace
 
@@ -86,7 +120,7 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
         if (iso) for (int o = 0; o < n_obs; o++) obs[(size_t)c * n_obs + o] = lab->obs_time[o];
     }
 
-    DevBuf d_final, d_obs, d_esteps, d_status, d_ws;
+    DevBuf d_final, d_obs, d_esteps, d_status;
     if (!d_final.alloc(sizeof(int32_t) * R) || !d_esteps.alloc(sizeof(int64_t) * R) || !d_status.alloc(sizeof(int32_t) * R) ||
         !d_obs.alloc(sizeof(int32_t) * obs.size())) { set_error("mcl_objective: cudaMalloc failed"); return MCL_ERR_ALLOC; }
     mcl_run_args a;
@@ -101,8 +135,9 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
     a.stream = stream;
     size_t need = mcl_workspace_bytes(&a);
     if (!need) return MCL_ERR_ARG;
-    if (!d_ws.alloc(need)) { set_error("mcl_objective: cudaMalloc(workspace %zu) failed", need); return MCL_ERR_ALLOC; }
-    a.workspace = d_ws.p; a.workspace_bytes = need;
+    void *scratch = g_scratch.get(need);
+    if (!scratch) { set_error("mcl_objective: cudaMalloc(workspace %zu) failed", need); return MCL_ERR_ALLOC; }
+    a.workspace = scratch; a.workspace_bytes = need;
     int rc = mcl_run(&a);
     if (rc) return rc;
 
@@ -142,3 +177,5 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
     if (esteps_total) *esteps_total = total;
     return MCL_OK;
 }
+
+extern "C" void mcl_release_scratch(void) { g_scratch.release(); }

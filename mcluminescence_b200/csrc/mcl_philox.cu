@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *cr = reinterpret_cast<float *>(smem_raw);                  // [cap_slots]
     NearT *near = reinterpret_cast<NearT *>(cr + cfg.cap_slots);      // [cap_slots]
-    uint32_t *hole_bm = reinterpret_cast<uint32_t *>(near + cfg.cap_slots);   // [bm_words] 1 = initial hole alive
+    uint32_t *hole_bm = reinterpret_cast<uint32_t *>(near + cfg.cap_slots);   // [bm_words] 1 = hole slot alive
     __shared__ float red_v[2][32];
     __shared__ int red_s[2][32];
     __shared__ int red_h[2][32];
@@ -387,7 +387,10 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     const int n_cells = H.G * H.G * H.G;
 
     for (int s = tid; s < cfg.cap_slots; s += NT) { cr[s] = F_INF; near[s] = (NearT)NEAR_DEAD; }
-    for (int w = tid; w < cfg.bm_words; w += NT) hole_bm[w] = 0xffffffffu;
+    for (int w = tid; w < cfg.bm_words; w += NT) {          // slots [0, n_h0) start alive, the fill region empty
+        const int lo = 32 * w;
+        hole_bm[w] = lo + 32 <= rp.n_h0 ? 0xffffffffu : (lo >= rp.n_h0 ? 0u : ((1u << (rp.n_h0 - lo)) - 1u));
+    }
 
     if (status == MCL_OK) {
         // ---------------- Box.seed (engine.py:124-129): holes, binned into the cell grid
@@ -716,7 +719,11 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 if (ever_filled) {
                     // stale-cache mode: the reference also refreshes electrons cached on the hole that
                     // FOLLOWS the removed one in index order (shift-then-mask, engine.py:168-171)
-                    for (int j = h + 1; j < H.n_slots; j++) if (hpos[j].x < 1e29f) { h2 = j; break; }
+                    const int last_w = (H.n_slots - 1) >> 5;
+                    int w_ = (h + 1) >> 5;
+                    uint32_t bits = w_ <= last_w ? (hole_bm[w_] & (0xffffffffu << ((h + 1) & 31))) : 0u;
+                    while (!bits && w_ < last_w) bits = hole_bm[++w_];
+                    if (bits) { const int j = 32 * w_ + __ffs(bits) - 1; if (j < H.n_slots) h2 = j; }
                 }
                 if (tid == 0) {
                     hpos[h].x = DEAD_X;
@@ -724,7 +731,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     // (retarget below, other warps) skips hole h before it looks at a word: reading the old or the
                     // new word gives the same answer.  compute-sanitizer racecheck flags exactly this read / RMW
                     // overlap; it is benign by construction.  The next barrier publishes the bit.
-                    if (h < n_h0) hole_bm[h >> 5] &= ~(1u << (h & 31));
+                    hole_bm[h >> 5] &= ~(1u << (h & 31));
                     if (hist_on && p.hist_events) {
                         // edges up to t_cur have been passed: the event sits in the bin before the cursor
                         const int b = h_mono ? (hbin_next - 1) : bin_of(t_cur);
@@ -877,7 +884,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         hs = -1;
                         for (int base = n_h0; base < H.n_slots && hs < 0; base += 32) {
                             int j = base + lane;
-                            unsigned m = __ballot_sync(0xffffffffu, j < H.n_slots && !(hpos[j].x < 1e29f));
+                            unsigned m = __ballot_sync(0xffffffffu, j < H.n_slots && !((hole_bm[j >> 5] >> (j & 31)) & 1u));
                             if (m) hs = base + __ffs(m) - 1;
                         }
                     }
@@ -891,6 +898,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         ex[es] = nx; ey[es] = ny; ez[es] = nz;
                         cr[es] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[es] = (NearT)(uint32_t)b;
                         hpos[hs] = make_float4(qx, qy, qz, __int_as_float(hs));
+                        hole_bm[hs >> 5] |= 1u << (hs & 31);
                     }
                 }
                 if (append_e) n_slots++;
