@@ -965,6 +965,7 @@ static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override, int n_replica
     pl.g_max = grid_edge_max(cap_h);          // n_h0 <= cap_h: always enough room for the cell tables
     pl.cap_cells = pl.g_max * pl.g_max * pl.g_max + 1;
     pl.near16 = cap_h <= 65534;
+    if (const char *env = getenv("MCL_PHILOX_NEAR32")) { if (atoi(env) == 1) pl.near16 = false; }   // test knob: force the 32-bit slot path
     pl.bm_words = (cap_h + 31) / 32;
     pl.smem = (size_t)pl.cap_slots * (4 + (pl.near16 ? 2 : 4)) + 4 * (size_t)pl.bm_words;
     pl.off_holes = align_up(sizeof(float) * 3 * (size_t)cap_e, 16);

@@ -223,3 +223,33 @@ def test_objective_statistics_across_the_parameter_bounds(gpu, capsys):
             se = np.sqrt(g[:, k].var(ddof=1) / M + o[:, k].var(ddof=1) / M)
             assert abs(g[:, k].mean() - o[:, k].mean()) <= 4.5 * se + 0.35, (c, k, g[:, k].mean(), o[:, k].mean(), se)
     capsys.readouterr()
+
+
+def test_32_bit_nearest_slot_path_gives_identical_results(gpu):
+    """Boxes with more than 65534 hole slots keep 32-bit nearest-hole slots in shared memory; forcing that
+    instantiation on small boxes must not change a single record (simulate legs, histograms, lab rows with fills)."""
+    import os
+    from mcluminescence_b200 import engine
+    from mcluminescence_b200.config import compose, initialize_runs
+    from mcluminescence_b200.replicas import LAB_CSV, LabTable
+    wl = two_leg_workload(R=40, n_e=600)
+    run = initialize_runs(compose(overrides=helpers.LAB_OVERRIDES))[0]
+    lt = LabTable(*LAB_CSV["iso"], helpers.DATA_ROOT)
+    lab_reps, lab_segs = lt.tables(run)
+
+    def both():
+        a = engine.run_replicas(wl["replicas"], wl["segments"], wl["max_steps"], seed=9, hist=wl["hist"], trace=True, sync=True)
+        b = engine.run_replicas(lab_reps, lab_segs, 20000, seed=9, obs_time=lt.obs_time, trace=True, sync=True)
+        return a, b
+    a16, b16 = both()
+    os.environ["MCL_PHILOX_NEAR32"] = "1"
+    try:
+        a32, b32 = both()
+    finally:
+        del os.environ["MCL_PHILOX_NEAR32"]
+    for x, y in ((a16, a32), (b16, b32)):
+        x.raise_on_error(); y.raise_on_error()
+        assert np.array_equal(x.event, y.event) and np.array_equal(x.n_e, y.n_e) and np.array_equal(x.t, y.t)
+        assert np.array_equal(x.esteps, y.esteps)
+    assert np.array_equal(a16.hist_events, a32.hist_events) and np.array_equal(a16.hist_occ, a32.hist_occ)
+    assert np.array_equal(b16.obs_n_e, b32.obs_n_e)
