@@ -1011,14 +1011,10 @@ cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_
     uint32_t k0 = (uint32_t)s, k1 = (uint32_t)(s >> 32);
     for (int r = 0; r < 10; r++) { K.k[2 * r] = k0; K.k[2 * r + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
     // MINB caps the register count at 64 per thread (32 resident warps per SM when smem allows)
-#define MCL_GO(NT_, MINB_, PPC_)                                                                    \
-    (pl.near16 ? launch_one<NT_, MINB_, uint16_t, PPC_>(p, K, cfg, pl.smem, stream)                \
-               : launch_one<NT_, MINB_, uint32_t, PPC_>(p, K, cfg, pl.smem, stream))
 #define MCL_CASE(NT_, MINB_, PPC_)                                                                  \
     case NT_:                                                                                      \
-        return (ppc_override ? ppc_override : PPC_) == 2 ? MCL_GO(NT_, MINB_, 2) : MCL_GO(NT_, MINB_, 1)
-    int ppc_override = 0;
-    if (const char *env = getenv("MCL_PHILOX_PPC")) { int v = atoi(env); if (v == 1 || v == 2) ppc_override = v; }   // tuning knob
+        return pl.near16 ? launch_one<NT_, MINB_, uint16_t, PPC_>(p, K, cfg, pl.smem, stream)      \
+                         : launch_one<NT_, MINB_, uint32_t, PPC_>(p, K, cfg, pl.smem, stream)
     switch (pl.nt) {
         MCL_CASE(32, 32, 1);
         MCL_CASE(64, 16, 1);
@@ -1026,8 +1022,8 @@ cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_
         MCL_CASE(256, 3, 2);
         default: break;
     }
-    return (ppc_override ? ppc_override : 2) == 2 ? MCL_GO(512, 2, 2) : MCL_GO(512, 2, 1);
-#undef MCL_GO
+    return pl.near16 ? launch_one<512, 2, uint16_t, 2>(p, K, cfg, pl.smem, stream)
+                     : launch_one<512, 2, uint32_t, 2>(p, K, cfg, pl.smem, stream);
 #undef MCL_CASE
 }
 
