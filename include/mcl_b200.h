@@ -45,6 +45,7 @@ extern "C" {
 #define MCL_ERR_ARG       -6
 #define MCL_ERR_CUDA      -7
 #define MCL_ERR_CAPACITY  -8   /* replica does not fit the kernel's per-block capacity              */
+#define MCL_ERR_INTERNAL  -9   /* a kernel self-check failed (test modes only)                       */
 
 /* One leg of a temperature / dose schedule.  The reference has exactly one per replica
  * (simulate.py:40-45,53-54); several legs chain irradiation -> hold -> readout on one box. */

@@ -53,7 +53,8 @@ struct Cfg {
     int cap_slots;     // even; smem slots per replica
     int g_max;         // largest grid edge the slab has room for
     int cap_cells;     // g_max^3 + 1
-    int bm_words;      // smem words of the initial-hole alive bitmap
+    int bm_words;      // smem words of the hole alive bitmap
+    int share_bm;      // 1: two more bitmaps (hole targeted by >= 1 / >= 2 electrons) let events skip the scan
     size_t off_holes;  // byte offset of the hole table inside the slab (16-byte aligned)
     size_t off_cand;   // byte offset of the candidate lists inside the slab
 };
@@ -353,6 +354,15 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     float *cr = reinterpret_cast<float *>(smem_raw);                  // [cap_slots]
     NearT *near = reinterpret_cast<NearT *>(cr + cfg.cap_slots);      // [cap_slots]
     uint32_t *hole_bm = reinterpret_cast<uint32_t *>(near + cfg.cap_slots);   // [bm_words] 1 = hole slot alive
+    // Optional: seen_bm / multi_bm = hole is the cached nearest of >= 1 / >= 2 electrons.  Electrons leave a hole
+    // only when it dies, so for an ALIVE hole these are exact counts (capped at 2) as long as no electron is added.
+    uint32_t *seen_bm = hole_bm + cfg.bm_words, *multi_bm = seen_bm + cfg.bm_words;
+    const bool share_bm = cfg.share_bm != 0;
+    const bool verify_skip = cfg.share_bm == 2;     // test mode: scan anyway and flag a hit that the bitmaps ruled out
+    auto mark_target = [&](uint32_t j) {
+        const uint32_t bit = 1u << (j & 31);
+        if (atomicOr(&seen_bm[j >> 5], bit) & bit) atomicOr(&multi_bm[j >> 5], bit);
+    };
     __shared__ float red_v[2][32];
     __shared__ int red_s[2][32];
     __shared__ int red_h[2][32];
@@ -360,6 +370,8 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     __shared__ int rec_ev[32], rec_ne[32];
     __shared__ double rec_t[32];
     __shared__ int s_scan[33];
+    __shared__ int s_err;              // self-check failures (verify mode)
+    if (threadIdx.x == 0) s_err = 0;
 
     // ---------------- HBM slab
     unsigned char *ws = p.ws + (size_t)r * p.ws_stride;
@@ -500,9 +512,14 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         cta_sync<NT>();
         // ---------------- Box._rebuild (engine.py:113-119): the KC nearest holes of every electron (kept out of
         // line so that its register needs do not disturb the allocation of the step loop)
+        if (share_bm) for (int w = tid; w < 2 * cfg.bm_words; w += NT) seen_bm[w] = 0u;
         if (NT >= 256) seed_candidate_lists_call<NearT>(H, cell_fill, ex, ey, ez, cand_d, cand_j, cr, near, n_cells, warp, lane, NW);
         else seed_candidate_lists_impl<NearT>(H, cell_fill, ex, ey, ez, cand_d, cand_j, cr, near, n_cells, warp, lane, NW);
         cta_sync<NT>();
+        if (share_bm) {
+            for (int i = tid; i < n_e; i += NT) { const uint32_t j = near[i]; if (j != NEAR_DEAD) mark_target(j); }
+            cta_sync<NT>();
+        }
     }
 
     // ---------------- per-replica constants of the rate law, log2 domain
@@ -742,6 +759,8 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 // Which of MY other electrons were cached on h (or h2)?  A thread owns the pairs it sweeps
                 // (q = tid, tid + NT, ...), and only the owner ever touches cr[] / near[] of a pair outside
                 // barrier-protected phases -- so re-targeting needs no CTA barrier at all.
+                // no other electron can be cached on h if h was never the target of a second one
+                const bool lone = share_bm && !ever_filled && !((multi_bm[h >> 5] >> (h & 31)) & 1u);
                 int redo = -1;                      // a slot of mine that needs the warp-cooperative search
                 auto retarget = [&](int sl) {
                     bool fixed = false;
@@ -755,6 +774,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                             const uint32_t j = cand_j[(size_t)sl * KC + c];
                             if (!fixed && j != NEAR_DEAD && j != (uint32_t)h && ((hole_bm[j >> 5] >> (j & 31)) & 1u)) {
                                 cr[sl] = dk[c]; near[sl] = (NearT)j; fixed = true;
+                                if (share_bm) mark_target(j);
                             }
                         }
                     }
@@ -786,6 +806,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                             for (int k = 0; k < SPC; k++) {
                                 const int sl = SPC * b + k;
                                 const uint32_t nn = near[sl];
+                                if ((nn == (uint32_t)h || (TWO && nn == (uint32_t)h2)) && sl != smin && lone) atomicOr(&s_err, 1);
                                 if ((nn == (uint32_t)h || (TWO && nn == (uint32_t)h2)) && sl != smin && !retarget(sl)) {
                                     // rare: park it until the warp search below
                                     if (redo >= 0) cr[sl] = -1.0f;      // more than one: mark, found again below
@@ -795,7 +816,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         }
                     }
                 };
-                if (h2 >= 0) scan(std::true_type{}); else scan(std::false_type{});
+                if (!lone || verify_skip) { if (h2 >= 0) scan(std::true_type{}); else scan(std::false_type{}); }
                 // Exhausted lists and fill mode (new holes become visible on a re-search, engine.py:171-175):
                 // the owner's WARP searches the cell grid cooperatively; still no CTA barrier.
                 {
@@ -807,6 +828,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         unsigned long long b = warp_nearest(H, ex[sl], ey[sl], ez[sl], lane, h);
                         if (lane == src) {
                             cr[sl] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[sl] = (NearT)(uint32_t)b;
+                            if (share_bm && !ever_filled) mark_target((uint32_t)b);
                             // further parked slots of this lane were marked with cr = -1
                             redo = -1;
                             for (int b = tid; b < n_chunks && redo < 0; b += NT)
@@ -925,6 +947,8 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     }
     flush_records(rec_i & 31);
     if (status == MCL_OK && rp.protocol == MCL_PROTO_TL_LAB && rec_i == 0) status = MCL_ERR_NOEVENT;
+    cta_sync<NT>();
+    if (s_err && status == MCL_OK) status = MCL_ERR_INTERNAL;
     if (tid == 0) {
         if (p.steps_used) p.steps_used[r] = rec_i;
         if (p.final_n_e) p.final_n_e[r] = n_e;
@@ -953,7 +977,7 @@ static int grid_edge_max(int n_h0_max)
     return g < 1 ? 1 : g;
 }
 
-struct PhiloxPlan { int nt; int cap_slots; int g_max; int cap_cells; int bm_words; size_t smem; size_t off_holes; size_t off_cand; size_t stride; bool near16; };
+struct PhiloxPlan { int nt; int cap_slots; int g_max; int cap_cells; int bm_words; int share_bm; size_t smem; size_t off_holes; size_t off_cand; size_t stride; bool near16; };
 
 static int g_nt_override = 0;
 void philox_set_block_threads(int nt) { g_nt_override = nt; }
@@ -985,6 +1009,10 @@ static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override, int n_replica
     if (nt_override == 32 || nt_override == 64 || nt_override == 128 || nt_override == 256 || nt_override == 512)
         nt = nt_override;
     pl.nt = nt;
+    // large boxes have the shared memory to spare (they are limited to 3 CTAs per SM either way)
+    pl.share_bm = nt >= 256 ? 1 : 0;
+    if (const char *env = getenv("MCL_PHILOX_SHARE_BM")) { int v = atoi(env); pl.share_bm = v < 0 ? 0 : (v > 2 ? 2 : v); }   // knob: 0 off, 1 on, 2 on + self-check
+    if (pl.share_bm) pl.smem += 2 * 4 * (size_t)pl.bm_words;
     return pl;
 }
 
@@ -1005,7 +1033,7 @@ static cudaError_t launch_one(const LaunchParams &p, const RoundKeys &K, const C
 cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_slots*/)
 {
     PhiloxPlan pl = make_plan(p.cap_e, p.cap_h, g_nt_override, p.n_replicas);
-    Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.off_holes, pl.off_cand};
+    Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.share_bm, pl.off_holes, pl.off_cand};
     RoundKeys K;
     uint64_t s = mix64(p.seed);
     uint32_t k0 = (uint32_t)s, k1 = (uint32_t)(s >> 32);

@@ -42,6 +42,7 @@ STATUS_MESSAGES = {
     -6: "bad argument",
     -7: "CUDA error",
     -8: "replica does not fit the kernel's per-block capacity",
+    -9: "kernel self-check failed",
 }
 
 

@@ -253,3 +253,23 @@ def test_32_bit_nearest_slot_path_gives_identical_results(gpu):
         assert np.array_equal(x.esteps, y.esteps)
     assert np.array_equal(a16.hist_events, a32.hist_events) and np.array_equal(a16.hist_occ, a32.hist_occ)
     assert np.array_equal(b16.obs_n_e, b32.obs_n_e)
+
+
+@pytest.mark.parametrize("which", ["c2", "c5"])
+def test_scan_skip_bitmaps_never_hide_a_cached_electron(gpu, which):
+    """Self-check mode: events whose post-event scan the sharing bitmaps would skip are scanned anyway and any hit
+    is reported as MCL_ERR_INTERNAL.  Also: skipping changes no record."""
+    import os
+    from mcluminescence_b200 import engine, workloads
+    wl = workloads.c2(n_replicas=32, n_e=6000) if which == "c2" else workloads.c5(n_replicas=64)
+    runs = {}
+    for mode in ("0", "1", "2"):
+        os.environ["MCL_PHILOX_SHARE_BM"] = mode
+        try:
+            runs[mode] = engine.run_replicas(wl["replicas"], wl["segments"], wl["max_steps"], seed=23, trace=True, sync=True)
+        finally:
+            del os.environ["MCL_PHILOX_SHARE_BM"]
+        assert not runs[mode].status.any(), (mode, runs[mode].status[runs[mode].status != 0][:4])
+    for mode in ("1", "2"):
+        assert np.array_equal(runs[mode].event, runs["0"].event) and np.array_equal(runs[mode].n_e, runs["0"].n_e)
+        assert np.array_equal(runs[mode].t, runs["0"].t)
