@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     __shared__ float red_v[2][32];
     __shared__ int red_s[2][32];
     __shared__ int red_h[2][32];
-    __shared__ uint32_t stepdraw[2][4];
+    __shared__ uint32_t stepdraw[2][32][4];     // step scalars of 32 consecutive steps, double-buffered per block of 32
     __shared__ int rec_ev[32], rec_ne[32];
     __shared__ double rec_t[32];
     __shared__ int s_scan[33];
@@ -538,6 +538,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     int n_slots = n_e;             // electron slots in use (alive or tombstoned)
     int n_fill_alive = 0;          // alive holes in the fill region
     bool ever_filled = false;
+    bool draws_valid = false;      // stepdraw holds the block of 32 steps that contains rec_i
     int rec_i = 0;
     long long esteps = 0;
     double t_off = 0.0;
@@ -669,14 +670,17 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 __syncwarp();
                 if (lane == 0) { red_v[par][warp] = wv; red_s[par][warp] = ws_; red_h[par][warp] = ws_ >= 0 ? (int)near[ws_] : -1; }
             }
-            if (warp == 0) {
-                // step scalars: fill clock + coordinates of a would-be new electron / hole
-                uint32_t c0 = 0u, c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_SCALAR << 28);
+            if (warp == 0 && ((rec_i & 31) == 0 || !draws_valid)) {
+                // step scalars (fill clock + coordinates of a would-be new electron) of the 32 steps of this block
+                // of records, one Philox call per lane: counter-based, so step k gets the same words as if it were
+                // drawn on its own.  Double-buffered: the other buffer may still be read by a warp that is late in
+                // the previous step.
+                uint32_t c0 = 0u, c1 = (uint32_t)((rec_i & ~31) + lane), c2 = rid_lo, c3 = rid_hi | (DOM_SCALAR << 28);
                 philox4x32_10(c0, c1, c2, c3, K);
-                if (lane == 0) {
-                    stepdraw[par][0] = c0; stepdraw[par][1] = c1; stepdraw[par][2] = c2; stepdraw[par][3] = c3;
-                }
+                uint32_t *d = stepdraw[(rec_i >> 5) & 1][lane];
+                d[0] = c0; d[1] = c1; d[2] = c2; d[3] = c3;
             }
+            draws_valid = true;
             cta_sync<NT>();                                   // ===== B1
             float vmin; int smin, hmin;
             {
@@ -693,7 +697,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             float dt_fill;
             {
                 float lam = (n_e == rp.N_e || !dose_on) ? 1e-20f : dose_over_D0 * (float)(rp.N_e - n_e);
-                dt_fill = lam > 0.0f ? (-lg2_fast(u01(stepdraw[par][0])) * LN2F) / lam : 1e20f;
+                dt_fill = lam > 0.0f ? (-lg2_fast(u01(stepdraw[(rec_i >> 5) & 1][rec_i & 31][0])) * LN2F) / lam : 1e20f;
             }
             const float dt_rec = n_e > 0 ? ex2_fast(vmin) * LN2F : dt_fill;
             float dt; bool is_fill, is_rec;
@@ -910,8 +914,8 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                             if (m) hs = base + __ffs(m) - 1;
                         }
                     }
-                    float nx = u01(stepdraw[par][1]) * core_s, ny = u01(stepdraw[par][2]) * core_s,
-                          nz = u01(stepdraw[par][3]) * core_s;
+                    const uint32_t *sd = stepdraw[(rec_i >> 5) & 1][rec_i & 31];
+                    float nx = u01(sd[1]) * core_s, ny = u01(sd[2]) * core_s, nz = u01(sd[3]) * core_s;
                     uint32_t d0 = 1u, d1 = (uint32_t)rec_i, d2 = rid_lo, d3 = rid_hi | (DOM_SCALAR << 28);
                     philox4x32_10(d0, d1, d2, d3, K);
                     float qx = u01(d0) * bnd_s, qy = u01(d1) * bnd_s, qz = u01(d2) * bnd_s;
