@@ -38,10 +38,10 @@ SFU_PER_ESTEP = 3.0
 LANEOPS_PER_ESTEP = 45.0
 
 
-def build_workload(name: str, replicas: int):
+def build_workload(name: str, replicas: int, electrons: int = 0):
     from mcluminescence_b200 import workloads
     if name == "c2":
-        return workloads.c2(n_replicas=replicas)
+        return workloads.c2(n_replicas=replicas, n_e=electrons) if electrons > 0 else workloads.c2(n_replicas=replicas)
     if name == "c5":
         return workloads.c5(n_replicas=replicas)
     if name == "c1":
@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c1"])
     ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU per step (0 = workload default)")
+    ap.add_argument("--electrons", type=int, default=0, help="tuning only: electrons per replica of the C2 shape")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -177,7 +178,7 @@ def main():
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
 
-    wl = build_workload(args.workload, args.replicas)
+    wl = build_workload(args.workload, args.replicas, args.electrons)
     peaks = engine.device_peaks()
 
     def barrier():
