@@ -41,7 +41,10 @@ namespace {
 
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
-constexpr uint32_t DOM_STEP = 0u, DOM_SCALAR = 1u, DOM_SEED_E = 2u, DOM_SEED_H = 3u;
+constexpr uint32_t DOM_STEP = 0u, DOM_SCALAR = 1u, DOM_SEED_E = 2u, DOM_SEED_H = 3u, DOM_STEP1 = 4u;
+#ifndef MCL_ONE_CHAINS
+#define MCL_ONE_CHAINS 2
+#endif
 constexpr float F_INF = __builtin_huge_valf();
 constexpr float DEAD_X = 1e30f;
 constexpr float LN2F = 0.69314718055994530942f;
@@ -343,6 +346,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     constexpr int NW = NT / 32;
     constexpr uint32_t NEAR_DEAD = NearTraits<NearT>::DEAD;
     constexpr int SPC = 2 * PPC;              // slots per chunk: a thread owns whole chunks (chunk b -> thread b % NT)
+    static_assert(PPC == 2, "a chunk is four slots: one 16-byte load of cr[], one Philox call when the channels are identical");
     const int r = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const mcl_replica rp = p.replicas[r];
@@ -594,6 +598,26 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         double hedge_next = CUDART_INF;
         if (h_mono) hedge_next = h_log ? p.hist.lo : edge_after(0, 0.0);
 
+        // Rate-law prefactors at temperature T(t) (log2 domain).  Isothermal legs (C2, ISO_lab) evaluate them once.
+        float A1, A2, g; bool has_cb;
+        const bool T_const = (lab && iso) || S.T_rate == 0.0;
+        auto set_T = [&](double t) {
+            const float T_now = (float)((lab && iso) ? T0K : (S.T_start + S.T_rate * t + 273.15));
+            float invT;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(invT) : "f"(T_now));
+            A1 = fmaf(-eb1, invT, lb); A2 = fmaf(-eb2, invT, lb);
+            if (A_opt != 0.0f) {       // (A_opt + b e^{-E/kT}) e^{-alpha r}: fold the sum into the prefactor
+                A1 = lg2_fast(A_opt + ex2_fast(A1));
+                A2 = lg2_fast(A_opt + ex2_fast(A2));
+            }
+            if (one_ch_2) A1 = A2;
+            if (one_ch_1) A2 = A1;
+            g = fmaf(-ecb, invT, ls);                                   // lg2 k_cb
+            // conduction-band channel can be skipped when it is < 2^-30 of the slowest tunnelling rate
+            has_cb = g > fminf(A1, A2) - cr_far - 30.0f;
+        };
+        set_T(0.0);
+
         for (;;) {
             // ---------------- loop condition (simulate.py:51; tl_trap_lab.py:90,147)
             if (!lab) { if (!(t_cur <= S.duration)) break; }
@@ -602,61 +626,86 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             if (rec_i >= p.max_steps) { status = MCL_ERR_STEPS; break; }
 
             // ---------------- temperature-dependent scalars (uniform; FP32 from an FP64 clock)
-            const float T_now = (float)((lab && iso) ? T0K : (S.T_start + S.T_rate * t_cur + 273.15));
-            const float invT = __frcp_rn(T_now);
-            float A1 = fmaf(-eb1, invT, lb), A2 = fmaf(-eb2, invT, lb);
-            if (A_opt != 0.0f) {       // (A_opt + b e^{-E/kT}) e^{-alpha r}: fold the sum into the prefactor
-                A1 = lg2_fast(A_opt + ex2_fast(A1));
-                A2 = lg2_fast(A_opt + ex2_fast(A2));
-            }
-            if (one_ch_2) A1 = A2;
-            if (one_ch_1) A2 = A1;
-            const float g = fmaf(-ecb, invT, ls);                       // lg2 k_cb
-            // conduction-band channel can be skipped when it is < 2^-30 of the slowest tunnelling rate
-            const bool has_cb = g > fminf(A1, A2) - cr_far - 30.0f;
+            if (!T_const) set_T(t_cur);
             const int par = rec_i & 1;
 
             // ---------------- per-electron clocks + running argmin
             float best = F_INF; int bslot = -1;
-            // A thread owns whole CHUNKS of SPC slots (chunk b = slots SPC*b.. belongs to thread b % NT).  With
-            // PPC = 2 one 16-byte load feeds two independent Philox calls and the post-event scan reads the
-            // chunk's four nearest-hole slots with one load; PPC = 1 keeps the granularity fine for small boxes.
+            // A thread owns whole CHUNKS of SPC = 4 slots (chunk b = slots 4b.. belongs to thread b % NT): one 16-byte
+            // load feeds the clocks of a chunk and the post-event scan reads its nearest-hole slots with one load.
             const int n_chunks = (n_slots + SPC - 1) / SPC;
             auto pair_loop = [&](auto with_cb, auto one_channel) {
                 constexpr bool CB = decltype(with_cb)::value;
                 constexpr bool ONE = decltype(one_channel)::value;     // both tunnelling channels identical
-                for (int b = tid; b < n_chunks; b += NT) {
-                    float cs[SPC];
-                    if (PPC == 2) {
-                        const float4 cq = reinterpret_cast<const float4 *>(cr)[b];
-                        cs[0] = cq.x; cs[1] = cq.y; cs[SPC - 2] = cq.z; cs[SPC - 1] = cq.w;
-                    } else {
-                        const float2 cq = reinterpret_cast<const float2 *>(cr)[b];
-                        cs[0] = cq.x; cs[1] = cq.y;
-                    }
-                    float l[SPC];
+                if constexpr (ONE) {
+                    // Identical channels: the selector draw cannot change anything, so no word is spent on it.  One
+                    // Philox call serves the FOUR slots of a chunk (word k -> slot 4b + k); MCL_ONE_CHAINS chunks of
+                    // the same owner per iteration keep that many independent Philox chains in flight.
+                    const float4 *cr4 = reinterpret_cast<const float4 *>(cr);
+                    auto chunks = [&](auto n_chains, int b0) {
+                        constexpr int NCH = decltype(n_chains)::value;
+                        float cs[NCH][4];
+                        uint32_t w[NCH][4];
 #pragma unroll
-                    for (int i = 0; i < PPC; i++) {
-                        uint32_t c0 = (uint32_t)(PPC * b + i), c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);
-                        philox4x32_10(c0, c1, c2, c3, K);
-                        // the selector draws (c0, c2) pick the channel; with identical channels the pick is moot
-                        const float a0 = (ONE ? A1 : ((c0 < thr) ? A2 : A1)) - cs[2 * i];
-                        const float a1 = (ONE ? A1 : ((c2 < thr) ? A2 : A1)) - cs[2 * i + 1];
-                        const float le0 = lg2_fast(-lg2_fast(u01(c1)));
-                        const float le1 = lg2_fast(-lg2_fast(u01(c3)));
-                        if (CB) {
-                            // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
-                            const float k0 = fmaxf(a0, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a0 - g)));
-                            const float k1 = fmaxf(a1, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a1 - g)));
-                            l[2 * i] = (le0 - k0) + (cs[2 * i] - cs[2 * i]);
-                            l[2 * i + 1] = (le1 - k1) + (cs[2 * i + 1] - cs[2 * i + 1]);
-                        } else {
-                            l[2 * i] = le0 - a0;
-                            l[2 * i + 1] = le1 - a1;
+                        for (int q = 0; q < NCH; q++) {
+                            const int b = b0 + q * NT;
+                            const float4 cq = cr4[b];
+                            cs[q][0] = cq.x; cs[q][1] = cq.y; cs[q][2] = cq.z; cs[q][3] = cq.w;
+                            w[q][0] = (uint32_t)b; w[q][1] = (uint32_t)rec_i; w[q][2] = rid_lo; w[q][3] = rid_hi | (DOM_STEP1 << 28);
                         }
-                    }
 #pragma unroll
-                    for (int i = 0; i < SPC; i++) if (l[i] < best) { best = l[i]; bslot = SPC * b + i; }
+                        for (int q = 0; q < NCH; q++) philox4x32_10(w[q][0], w[q][1], w[q][2], w[q][3], K);
+#pragma unroll
+                        for (int q = 0; q < NCH; q++) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const float le = lg2_fast(-lg2_fast(u01(w[q][k])));
+                                float l;
+                                if (CB) {
+                                    // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
+                                    const float a = A1 - cs[q][k];
+                                    const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
+                                    l = (le - kk) + (cs[q][k] - cs[q][k]);
+                                } else {
+                                    l = le + cs[q][k];              // the uniform prefactor A1 is subtracted after the loop
+                                }
+                                if (l < best) { best = l; bslot = 4 * (b0 + q * NT) + k; }
+                            }
+                        }
+                    };
+                    int b0 = tid;
+                    for (; b0 + (MCL_ONE_CHAINS - 1) * NT < n_chunks; b0 += MCL_ONE_CHAINS * NT)
+                        chunks(std::integral_constant<int, MCL_ONE_CHAINS>{}, b0);
+                    for (; b0 < n_chunks; b0 += NT) chunks(std::integral_constant<int, 1>{}, b0);       // tail: no wasted calls
+                    if (!CB) best -= A1;
+                } else {
+                    for (int b = tid; b < n_chunks; b += NT) {
+                        float cs[SPC];
+                        const float4 cq = reinterpret_cast<const float4 *>(cr)[b];
+                        cs[0] = cq.x; cs[1] = cq.y; cs[2] = cq.z; cs[3] = cq.w;
+                        float l[SPC];
+#pragma unroll
+                        for (int i = 0; i < PPC; i++) {
+                            uint32_t c0 = (uint32_t)(PPC * b + i), c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);
+                            philox4x32_10(c0, c1, c2, c3, K);
+                            // the selector draws (c0, c2) pick the channel
+                            const float a0 = ((c0 < thr) ? A2 : A1) - cs[2 * i];
+                            const float a1 = ((c2 < thr) ? A2 : A1) - cs[2 * i + 1];
+                            const float le0 = lg2_fast(-lg2_fast(u01(c1)));
+                            const float le1 = lg2_fast(-lg2_fast(u01(c3)));
+                            if (CB) {
+                                const float k0 = fmaxf(a0, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a0 - g)));
+                                const float k1 = fmaxf(a1, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a1 - g)));
+                                l[2 * i] = (le0 - k0) + (cs[2 * i] - cs[2 * i]);
+                                l[2 * i + 1] = (le1 - k1) + (cs[2 * i + 1] - cs[2 * i + 1]);
+                            } else {
+                                l[2 * i] = le0 - a0;
+                                l[2 * i + 1] = le1 - a1;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < SPC; i++) if (l[i] < best) { best = l[i]; bslot = SPC * b + i; }
+                    }
                 }
             };
             if (A1 == A2) { if (has_cb) pair_loop(std::true_type{}, std::true_type{}); else pair_loop(std::false_type{}, std::true_type{}); }
@@ -697,7 +746,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             float dt_fill;
             {
                 float lam = (n_e == rp.N_e || !dose_on) ? 1e-20f : dose_over_D0 * (float)(rp.N_e - n_e);
-                dt_fill = lam > 0.0f ? (-lg2_fast(u01(stepdraw[(rec_i >> 5) & 1][rec_i & 31][0])) * LN2F) / lam : 1e20f;
+                dt_fill = lam > 0.0f ? __fdividef(-lg2_fast(u01(stepdraw[(rec_i >> 5) & 1][rec_i & 31][0])) * LN2F, lam) : 1e20f;
             }
             const float dt_rec = n_e > 0 ? ex2_fast(vmin) * LN2F : dt_fill;
             float dt; bool is_fill, is_rec;
@@ -1048,9 +1097,9 @@ cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_
         return pl.near16 ? launch_one<NT_, MINB_, uint16_t, PPC_>(p, K, cfg, pl.smem, stream)      \
                          : launch_one<NT_, MINB_, uint32_t, PPC_>(p, K, cfg, pl.smem, stream)
     switch (pl.nt) {
-        MCL_CASE(32, 32, 1);
-        MCL_CASE(64, 16, 1);
-        MCL_CASE(128, 8, 1);
+        MCL_CASE(32, 32, 2);
+        MCL_CASE(64, 16, 2);
+        MCL_CASE(128, 8, 2);
         MCL_CASE(256, 3, 2);
         default: break;
     }
