@@ -1,4 +1,7 @@
-"""Per-CUDA-source-line share of executed warp instructions and stall samples from an .ncu-rep."""
+"""Per-CUDA-source-line share of executed warp instructions and stall samples from an .ncu-rep.
+
+    python scripts/ncu_lines.py <rep> [top_n] [samples]     # third argument: rank by stall samples instead of instructions
+"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
@@ -26,5 +29,5 @@ for r in rows:
             pass
 ts = sum(v[0] for v in lines.values()); ti = sum(v[1] for v in lines.values())
 print(f"total samples {ts}  warp-instructions {ti}")
-for (ln, src), (s, i, t) in sorted(lines.items(), key=lambda kv: -kv[1][1])[:top]:
+for (ln, src), (s, i, t) in sorted(lines.items(), key=lambda kv: -kv[1][0 if len(sys.argv) > 3 else 1])[:top]:
     print(f"L{ln:4d} inst {100*i/ti:5.1f}%  samples {100*s/ts:5.1f}%  thr/inst {t/max(i,1):4.1f}  {src[:90]}")
