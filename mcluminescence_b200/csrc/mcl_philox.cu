@@ -42,6 +42,12 @@ namespace {
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 constexpr uint32_t DOM_STEP = 0u, DOM_SCALAR = 1u, DOM_SEED_E = 2u, DOM_SEED_H = 3u, DOM_STEP1 = 4u;
+#ifndef MCL_SCAN_UNROLL
+#define MCL_SCAN_UNROLL 4
+#endif
+#ifndef MCL_SCAN_UNROLL_NARROW
+#define MCL_SCAN_UNROLL_NARROW 1
+#endif
 #ifndef MCL_ONE_CHAINS
 #define MCL_ONE_CHAINS 2
 #endif
@@ -51,6 +57,11 @@ constexpr float LN2F = 0.69314718055994530942f;
 constexpr double L2E = 1.4426950408889634074;
 
 struct RoundKeys { uint32_t k[20]; };
+#ifdef MCL_PROFILE_SKEW
+// Profiling build only (scripts/build_variant.sh skew -DMCL_PROFILE_SKEW; scripts/skew_probe.py): cycles per warp index
+// spent in the sweep / waiting at the step barrier / between the barrier and the next sweep, and the step count.
+__device__ unsigned long long g_prof[4][32];
+#endif
 
 struct Cfg {
     int cap_slots;     // even; smem slots per replica
@@ -367,9 +378,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         const uint32_t bit = 1u << (j & 31);
         if (atomicOr(&seen_bm[j >> 5], bit) & bit) atomicOr(&multi_bm[j >> 5], bit);
     };
-    __shared__ float red_v[2][32];
-    __shared__ int red_s[2][32];
-    __shared__ int red_h[2][32];
+    __shared__ int4 red_row[2][32];            // per warp: (bits of its minimum, the slot, the slot's hole, -)
     __shared__ uint32_t stepdraw[2][32][4];     // step scalars of 32 consecutive steps, double-buffered per block of 32
     __shared__ int rec_ev[32], rec_ne[32];
     __shared__ double rec_t[32];
@@ -388,6 +397,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     float4 *cand_d = reinterpret_cast<float4 *>(ws + cfg.off_cand);   // [cap_e] cr of the KC nearest initial holes
     NearT *cand_j = reinterpret_cast<NearT *>(cand_d + ce);           // [cap_e][KC] their slots (NEAR_DEAD = none)
 
+#ifdef MCL_PROFILE_SKEW
+    long long pf_sweep = 0, pf_wait = 0, pf_rest = 0, pf_steps = 0, pf_t = 0;
+#endif
     int status = MCL_OK;
     const float core_s = (float)(rp.side * rp.alpha * L2E);
     const float bnd_s = (float)(rp.side * rp.boundary_factor * rp.alpha * L2E);
@@ -629,6 +641,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             if (!T_const) set_T(t_cur);
             const int par = rec_i & 1;
 
+#ifdef MCL_PROFILE_SKEW
+            { const long long now = clock64(); if (pf_t) pf_rest += now - pf_t; pf_t = now; }
+#endif
             // ---------------- per-electron clocks + running argmin
             float best = F_INF; int bslot = -1;
             // A thread owns whole CHUNKS of SPC = 4 slots (chunk b = slots 4b.. belongs to thread b % NT): one 16-byte
@@ -717,7 +732,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 int src = m ? (__ffs(m) - 1) : 0;
                 int ws_ = __shfl_sync(0xffffffffu, bslot, src);
                 __syncwarp();
-                if (lane == 0) { red_v[par][warp] = wv; red_s[par][warp] = ws_; red_h[par][warp] = ws_ >= 0 ? (int)near[ws_] : -1; }
+                if (lane == 0) red_row[par][warp] = make_int4(__float_as_int(wv), ws_, ws_ >= 0 ? (int)near[ws_] : -1, 0);
             }
             if (warp == 0 && ((rec_i & 31) == 0 || !draws_valid)) {
                 // step scalars (fill clock + coordinates of a would-be new electron) of the 32 steps of this block
@@ -730,12 +745,18 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 d[0] = c0; d[1] = c1; d[2] = c2; d[3] = c3;
             }
             draws_valid = true;
+#ifdef MCL_PROFILE_SKEW
+            { const long long now = clock64(); pf_sweep += now - pf_t; pf_t = now; }
+#endif
             cta_sync<NT>();                                   // ===== B1
+#ifdef MCL_PROFILE_SKEW
+            { const long long now = clock64(); pf_wait += now - pf_t; pf_t = now; pf_steps++; }
+#endif
             float vmin; int smin, hmin;
             {
-                float v = lane < NW ? red_v[par][lane] : F_INF;
-                int s = lane < NW ? red_s[par][lane] : -1;
-                int hh = lane < NW ? red_h[par][lane] : -1;
+                const int4 row = lane < NW ? red_row[par][lane] : make_int4(__float_as_int(F_INF), -1, -1, 0);
+                const float v = __int_as_float(row.x);
+                const int s = row.y, hh = row.z;
                 vmin = warp_min_f32(v);
                 unsigned m = __ballot_sync(0xffffffffu, v == vmin);
                 const int src = m ? (__ffs(m) - 1) : 0;
@@ -820,11 +841,20 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     if (!ever_filled) {
                         // no hole was ever added: the new nearest is the first remembered candidate that is
                         // still alive (and is not the hole dying now, whose bitmap bit may not be visible yet)
+                        // distances and slots of the list are fetched together: ONE round trip to L2 / HBM
                         const float4 d4 = cand_d[sl];
+                        uint32_t cj[KC];
+                        if (sizeof(NearT) == 2) {
+                            const uint2 v = *reinterpret_cast<const uint2 *>(cand_j + (size_t)sl * KC);
+                            cj[0] = v.x & 0xffffu; cj[1] = v.x >> 16; cj[2] = v.y & 0xffffu; cj[3] = v.y >> 16;
+                        } else {
+                            const uint4 v = *reinterpret_cast<const uint4 *>(cand_j + (size_t)sl * KC);
+                            cj[0] = v.x; cj[1] = v.y; cj[2] = v.z; cj[3] = v.w;
+                        }
                         const float dk[KC] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
                         for (int c = 0; c < KC; c++) {
-                            const uint32_t j = cand_j[(size_t)sl * KC + c];
+                            const uint32_t j = cj[c];
                             if (!fixed && j != NEAR_DEAD && j != (uint32_t)h && ((hole_bm[j >> 5] >> (j & 31)) & 1u)) {
                                 cr[sl] = dk[c]; near[sl] = (NearT)j; fixed = true;
                                 if (share_bm) mark_target(j);
@@ -835,27 +865,48 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 };
                 auto scan = [&](auto two_targets) {
                     constexpr bool TWO = decltype(two_targets)::value;
-                    for (int b = tid; b < n_chunks; b += NT) {
-                        bool hit;
-                        constexpr int NWORD = SPC * (int)sizeof(NearT) / 4;       // 32-bit words of near[] per chunk
-                        uint32_t w[NWORD];
-                        if (NWORD == 4) { const uint4 v = reinterpret_cast<const uint4 *>(near)[b]; w[0] = v.x; w[1 % NWORD] = v.y; w[2 % NWORD] = v.z; w[3 % NWORD] = v.w; }
-                        else if (NWORD == 2) { const uint2 v = reinterpret_cast<const uint2 *>(near)[b]; w[0] = v.x; w[1 % NWORD] = v.y; }
-                        else w[0] = reinterpret_cast<const uint32_t *>(near)[b];
-                        if (sizeof(NearT) == 2) {
-                            // 16-bit slots: zero-halfword test (false positives possible, re-checked below)
-                            auto zh = [](uint32_t t) { return (t - 0x00010001u) & ~t & 0x80008000u; };
-                            const uint32_t hh = (uint32_t)h * 0x00010001u, hh2 = (uint32_t)h2 * 0x00010001u;
-                            uint32_t z = 0u;
+                    constexpr int NWORD = SPC * (int)sizeof(NearT) / 4;       // 32-bit words of near[] per chunk
+                    // chunks whose loads are in flight together (narrow CTAs: few chunks per thread, and their 16 CTAs per SM
+                    // at different phases feel every extra kilobyte of code in the instruction cache)
+                    constexpr int SU = NT >= 256 ? MCL_SCAN_UNROLL : MCL_SCAN_UNROLL_NARROW;
+                    const uint32_t hh = (uint32_t)h * 0x00010001u, hh2 = (uint32_t)h2 * 0x00010001u;
+                    for (int b0 = tid; b0 < n_chunks; b0 += SU * NT) {
+                        uint32_t w[SU][NWORD];
 #pragma unroll
-                            for (int k = 0; k < NWORD; k++) { z |= zh(w[k] ^ hh); if (TWO) z |= zh(w[k] ^ hh2); }
-                            hit = z != 0u;
-                        } else {
-                            hit = false;
+                        for (int u = 0; u < SU; u++) {
+                            const int b = b0 + u * NT;
+                            if (u > 0 && b >= n_chunks) {             // past the end: the empty-slot pattern matches no hole
 #pragma unroll
-                            for (int k = 0; k < NWORD; k++) { hit |= (w[k] == (uint32_t)h); if (TWO) hit |= (w[k] == (uint32_t)h2); }
+                                for (int k = 0; k < NWORD; k++) w[u][k] = 0xffffffffu;
+                            } else if (NWORD == 4) {
+                                const uint4 v = reinterpret_cast<const uint4 *>(near)[b];
+                                w[u][0] = v.x; w[u][1 % NWORD] = v.y; w[u][2 % NWORD] = v.z; w[u][3 % NWORD] = v.w;
+                            } else {
+                                const uint2 v = reinterpret_cast<const uint2 *>(near)[b];
+                                w[u][0] = v.x; w[u][1 % NWORD] = v.y;
+                            }
                         }
-                        if (hit) {
+                        uint32_t hits = 0u;                           // bit u: chunk b0 + u * NT may hold a match
+#pragma unroll
+                        for (int u = 0; u < SU; u++) {
+                            bool hit;
+                            if (sizeof(NearT) == 2) {
+                                // 16-bit slots: zero-halfword test (false positives possible, re-checked below)
+                                auto zh = [](uint32_t t) { return (t - 0x00010001u) & ~t & 0x80008000u; };
+                                uint32_t z = 0u;
+#pragma unroll
+                                for (int k = 0; k < NWORD; k++) { z |= zh(w[u][k] ^ hh); if (TWO) z |= zh(w[u][k] ^ hh2); }
+                                hit = z != 0u;
+                            } else {
+                                hit = false;
+#pragma unroll
+                                for (int k = 0; k < NWORD; k++) { hit |= (w[u][k] == (uint32_t)h); if (TWO) hit |= (w[u][k] == (uint32_t)h2); }
+                            }
+                            hits |= hit ? (1u << u) : 0u;
+                        }
+                        while (hits) {
+                            const int b = b0 + (__ffs(hits) - 1) * NT;
+                            hits &= hits - 1u;
                             for (int k = 0; k < SPC; k++) {
                                 const int sl = SPC * b + k;
                                 const uint32_t nn = near[sl];
@@ -998,6 +1049,12 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         t_off += t_cur;
         if (lab) break;
     }
+#ifdef MCL_PROFILE_SKEW
+    if (lane == 0) {
+        atomicAdd(&g_prof[0][warp], (unsigned long long)pf_sweep); atomicAdd(&g_prof[1][warp], (unsigned long long)pf_wait);
+        atomicAdd(&g_prof[2][warp], (unsigned long long)pf_rest); atomicAdd(&g_prof[3][warp], (unsigned long long)pf_steps);
+    }
+#endif
     flush_records(rec_i & 31);
     if (status == MCL_OK && rp.protocol == MCL_PROTO_TL_LAB && rec_i == 0) status = MCL_ERR_NOEVENT;
     cta_sync<NT>();
@@ -1023,6 +1080,16 @@ static inline uint64_t mix64(uint64_t z)
 }  // namespace
 
 int philox_max_slots() { return 24000; }
+
+#ifdef MCL_PROFILE_SKEW
+extern "C" int mcl_debug_prof(unsigned long long *out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 4 * 32);
+    if (reset) { static unsigned long long z[4 * 32]; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
+    return (int)e;
+}
+#endif
 
 static int grid_edge_max(int n_h0_max)
 {
