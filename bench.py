@@ -41,7 +41,8 @@ LANEOPS_PER_ESTEP = 45.0
 def build_workload(name: str, replicas: int, electrons: int = 0):
     from mcluminescence_b200 import workloads
     if name == "c2":
-        return workloads.c2(n_replicas=replicas, n_e=electrons) if electrons > 0 else workloads.c2(n_replicas=replicas)
+        kw = {"physics_overrides": ["physics_fp.E_loc_2=1.0", "physics_fp.Retrap=0.3"]} if os.environ.get("MCL_BENCH_TWO_CHANNEL") else {}
+        return workloads.c2(n_replicas=replicas, n_e=electrons, **kw) if electrons > 0 else workloads.c2(n_replicas=replicas, **kw)
     if name == "c5":
         return workloads.c5(n_replicas=replicas)
     if name == "c1":

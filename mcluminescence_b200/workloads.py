@@ -40,9 +40,11 @@ def _segments(*legs) -> np.ndarray:
     return segs
 
 
-def c2(n_replicas: int = 10_000, n_e: int = 10_000, n_bins: int = 1000):
+def c2(n_replicas: int = 10_000, n_e: int = 10_000, n_bins: int = 1000, physics_overrides=()):
+    """`physics_overrides` (e.g. two distinct tunnelling channels: ["physics_fp.E_loc_2=1.0", "physics_fp.Retrap=0.3"]) are for
+    side measurements only; the BASELINE workload uses the shipped basicTL12 physics."""
     cfg = compose(overrides=[f"exp_type_fp.N_e={n_e}", f"exp_type_fp.holes={n_e}",
-                             "exp_type_fp.T_rate=[0]", "exp_type_fp.duration=[1000]", "exp_type_fp.sims=1"])
+                             "exp_type_fp.T_rate=[0]", "exp_type_fp.duration=[1000]", "exp_type_fp.sims=1", *physics_overrides])
     run = initialize_runs(cfg)[0]
     rec = np.zeros(1, dtype=REPLICA_DTYPE)
     fill_replica(rec[0], run["exp_type_fp"], run["physics_fp"], 1.0, PROTO_SIMULATE)
