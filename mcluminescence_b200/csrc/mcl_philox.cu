@@ -68,7 +68,8 @@ struct Cfg {
     int g_max;         // largest grid edge the slab has room for
     int cap_cells;     // g_max^3 + 1
     int bm_words;      // smem words of the hole alive bitmap
-    int share_bm;      // 1: two more bitmaps (hole targeted by >= 1 / >= 2 electrons) let events skip the scan
+    int share_bm;      // 1: per-hole sharing masks (targeted by >= 2 electrons; by which warp groups) let events skip the scan
+    int ref_words;     // smem words of the warp-group reference mask (4 bits per hole)
     size_t off_holes;  // byte offset of the hole table inside the slab (16-byte aligned)
     size_t off_cand;   // byte offset of the candidate lists inside the slab
 };
@@ -370,14 +371,24 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     float *cr = reinterpret_cast<float *>(smem_raw);                  // [cap_slots]
     NearT *near = reinterpret_cast<NearT *>(cr + cfg.cap_slots);      // [cap_slots]
     uint32_t *hole_bm = reinterpret_cast<uint32_t *>(near + cfg.cap_slots);   // [bm_words] 1 = hole slot alive
-    // Optional: seen_bm / multi_bm = hole is the cached nearest of >= 1 / >= 2 electrons.  Electrons leave a hole
-    // only when it dies, so for an ALIVE hole these are exact counts (capped at 2) as long as no electron is added.
-    uint32_t *seen_bm = hole_bm + cfg.bm_words, *multi_bm = seen_bm + cfg.bm_words;
-    const bool share_bm = cfg.share_bm != 0;
-    const bool verify_skip = cfg.share_bm == 2;     // test mode: scan anyway and flag a hit that the bitmaps ruled out
-    auto mark_target = [&](uint32_t j) {
-        const uint32_t bit = 1u << (j & 31);
-        if (atomicOr(&seen_bm[j >> 5], bit) & bit) atomicOr(&multi_bm[j >> 5], bit);
+    // Optional (wide CTAs): ref4 = 4 bits per hole, bit g set when some slot OWNED BY WARP GROUP g (NW / 4 warps each) has
+    // the hole as its cached nearest; multi_bm = the hole is the cached nearest of >= 2 electrons.  Electrons leave a
+    // hole only when it dies, so for an ALIVE hole both are exact as long as no electron is added (stale ref4 bits of
+    // recombined electrons only cost a scan).  An event whose hole has no second electron skips the post-event scan
+    // altogether; otherwise only the warp groups that reference the hole scan.  Slot ownership changes in a
+    // compaction, which rebuilds ref4.
+    uint32_t *multi_bm = hole_bm + cfg.bm_words;                      // [bm_words]
+    uint32_t *ref4 = multi_bm + cfg.bm_words;                         // [ref_words] 8 holes per word
+    constexpr bool SHARE_K = NT >= 256;             // narrow CTAs never use the masks: keep their code out of those kernels
+    const bool share_bm = SHARE_K && cfg.share_bm != 0;
+    const bool verify_skip = SHARE_K && cfg.share_bm == 2;     // test mode: scan anyway and flag a hit that the masks ruled out
+    constexpr int GROUP_SHIFT = NW >= 4 ? (NW == 4 ? 0 : (NW == 8 ? 1 : 2)) : 0;      // warps per group = NW / 4 (NW >= 4)
+    const int my_group = min(3, warp >> GROUP_SHIFT);
+    auto group_of_slot = [&](int sl) { return min(3, (((sl >> 2) & (NT - 1)) >> 5) >> GROUP_SHIFT); };   // owner = chunk % NT
+    auto mark_target = [&](uint32_t j, int sl) {
+        const int sh = 4 * (j & 7);
+        const uint32_t old_ = atomicOr(&ref4[j >> 3], 1u << (sh + group_of_slot(sl)));
+        if ((old_ >> sh) & 0xfu) atomicOr(&multi_bm[j >> 5], 1u << (j & 31));      // somebody was there already
     };
     __shared__ int4 red_row[2][32];            // per warp: (bits of its minimum, the slot, the slot's hole, -)
     __shared__ uint32_t stepdraw[2][32][4];     // step scalars of 32 consecutive steps, double-buffered per block of 32
@@ -529,12 +540,12 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         cta_sync<NT>();
         // ---------------- Box._rebuild (engine.py:113-119): the KC nearest holes of every electron (kept out of
         // line so that its register needs do not disturb the allocation of the step loop)
-        if (share_bm) for (int w = tid; w < 2 * cfg.bm_words; w += NT) seen_bm[w] = 0u;
+        if (share_bm) for (int w = tid; w < cfg.bm_words + cfg.ref_words; w += NT) multi_bm[w] = 0u;
         if (NT >= 256) seed_candidate_lists_call<NearT>(H, cell_fill, ex, ey, ez, cand_d, cand_j, cr, near, n_cells, warp, lane, NW);
         else seed_candidate_lists_impl<NearT>(H, cell_fill, ex, ey, ez, cand_d, cand_j, cr, near, n_cells, warp, lane, NW);
         cta_sync<NT>();
         if (share_bm) {
-            for (int i = tid; i < n_e; i += NT) { const uint32_t j = near[i]; if (j != NEAR_DEAD) mark_target(j); }
+            for (int i = tid; i < n_e; i += NT) { const uint32_t j = near[i]; if (j != NEAR_DEAD) mark_target(j, i); }
             cta_sync<NT>();
         }
     }
@@ -558,6 +569,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     bool draws_valid = false;      // stepdraw holds the block of 32 steps that contains rec_i
     int rec_i = 0;
     long long esteps = 0;
+    uint32_t es32 = 0u;            // electron-steps since the last carry into `esteps`
     double t_off = 0.0;
     const size_t rec_base = (size_t)r * (size_t)p.max_steps;
     const bool trace = (p.event != nullptr) || (p.n_e != nullptr) || (p.t != nullptr);
@@ -765,12 +777,15 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 hmin = __shfl_sync(0xffffffffu, hh, src);
             }
             // ---------------- filling clock (tl_trap_lab.py:53-60) and dt (simulate.py:58-60)
-            float dt_fill;
-            {
+            // Without a dose the clock is exponential(1e20 s) >= -ln(1 - 2^-24) * 1e20 = 5.96e12 s: it can only matter (the
+            // reference's spurious fill) when nothing else happens before 5e12 s -- otherwise it is not evaluated.
+            const float dt_rec0 = n_e > 0 ? ex2_fast(vmin) * LN2F : F_INF;
+            float dt_fill = F_INF;
+            if (dose_on || !((lab ? dt_rec0 : fminf(dt_rec0, dt_cap)) < 5.0e12f)) {       // (the lab loops have no step cap)
                 float lam = (n_e == rp.N_e || !dose_on) ? 1e-20f : dose_over_D0 * (float)(rp.N_e - n_e);
                 dt_fill = lam > 0.0f ? __fdividef(-lg2_fast(u01(stepdraw[(rec_i >> 5) & 1][rec_i & 31][0])) * LN2F, lam) : 1e20f;
             }
-            const float dt_rec = n_e > 0 ? ex2_fast(vmin) * LN2F : dt_fill;
+            const float dt_rec = n_e > 0 ? dt_rec0 : dt_fill;
             float dt; bool is_fill, is_rec;
             if (!lab) {
                 dt = fminf(fminf(dt_fill, dt_rec), dt_cap);
@@ -781,7 +796,8 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 is_rec = !is_fill;
                 dt = is_fill ? dt_fill : dt_rec;
             }
-            esteps += n_e;
+            es32 += (uint32_t)n_e;
+            if (es32 > 0xC0000000u) { esteps += es32; es32 = 0u; }      // the 64-bit total lives in local memory
             const int n_before = n_e;
             const double t_new = t_cur + (double)dt;
 
@@ -835,7 +851,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 // (q = tid, tid + NT, ...), and only the owner ever touches cr[] / near[] of a pair outside
                 // barrier-protected phases -- so re-targeting needs no CTA barrier at all.
                 // no other electron can be cached on h if h was never the target of a second one
-                const bool lone = share_bm && !ever_filled && !((multi_bm[h >> 5] >> (h & 31)) & 1u);
+                const bool lone = share_bm && !ever_filled &&
+                                  (!((multi_bm[h >> 5] >> (h & 31)) & 1u) ||                    // nobody else at all, or
+                                   !((ref4[h >> 3] >> (4 * (h & 7) + my_group)) & 1u));         // nobody in MY warp group (warp-uniform)
                 int redo = -1;                      // a slot of mine that needs the warp-cooperative search
                 auto retarget = [&](int sl) {
                     bool fixed = false;
@@ -858,7 +876,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                             const uint32_t j = cj[c];
                             if (!fixed && j != NEAR_DEAD && j != (uint32_t)h && ((hole_bm[j >> 5] >> (j & 31)) & 1u)) {
                                 cr[sl] = dk[c]; near[sl] = (NearT)j; fixed = true;
-                                if (share_bm) mark_target(j);
+                                if (share_bm) mark_target(j, sl);
                             }
                         }
                     }
@@ -933,7 +951,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         unsigned long long b = warp_nearest(H, ex[sl], ey[sl], ez[sl], lane, h);
                         if (lane == src) {
                             cr[sl] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[sl] = (NearT)(uint32_t)b;
-                            if (share_bm && !ever_filled) mark_target((uint32_t)b);
+                            if (share_bm && !ever_filled) mark_target((uint32_t)b, sl);
                             // further parked slots of this lane were marked with cr = -1
                             redo = -1;
                             for (int b = tid; b < n_chunks && redo < 0; b += NT)
@@ -990,6 +1008,15 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     for (int s = run + tid; s < n_slots; s += NT) { cr[s] = F_INF; near[s] = (NearT)NEAR_DEAD; }
                     n_slots = run;
                     cta_sync<NT>();
+                    if (share_bm && !ever_filled) {           // slots changed owners: rebuild the warp-group reference mask
+                        for (int w = tid; w < cfg.ref_words; w += NT) ref4[w] = 0u;
+                        cta_sync<NT>();
+                        for (int sl = tid; sl < n_slots; sl += NT) {
+                            const uint32_t j = near[sl];
+                            if (j != NEAR_DEAD) atomicOr(&ref4[j >> 3], 1u << (4 * (j & 7) + group_of_slot(sl)));
+                        }
+                        cta_sync<NT>();
+                    }
                 }
             } else if (is_fill) {
                 // ---------------- Box.add_electron (engine.py:133-152), done by warp 0
@@ -1065,7 +1092,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     if (tid == 0) {
         if (p.steps_used) p.steps_used[r] = rec_i;
         if (p.final_n_e) p.final_n_e[r] = n_e;
-        if (p.esteps) p.esteps[r] = esteps;
+        if (p.esteps) p.esteps[r] = esteps + (long long)es32;
         if (p.consumed) p.consumed[r] = 0;
         if (p.status) p.status[r] = status;
     }
@@ -1100,7 +1127,7 @@ static int grid_edge_max(int n_h0_max)
     return g < 1 ? 1 : g;
 }
 
-struct PhiloxPlan { int nt; int cap_slots; int g_max; int cap_cells; int bm_words; int share_bm; size_t smem; size_t off_holes; size_t off_cand; size_t stride; bool near16; };
+struct PhiloxPlan { int nt; int cap_slots; int g_max; int cap_cells; int bm_words; int share_bm; int ref_words; size_t smem; size_t off_holes; size_t off_cand; size_t stride; bool near16; };
 
 static int g_nt_override = 0;
 void philox_set_block_threads(int nt) { g_nt_override = nt; }
@@ -1133,9 +1160,11 @@ static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override, int n_replica
         nt = nt_override;
     pl.nt = nt;
     // large boxes have the shared memory to spare (they are limited to 3 CTAs per SM either way)
-    pl.share_bm = nt >= 256 ? 1 : 0;
+    pl.share_bm = nt >= 256 ? 1 : 0;          // (the kernels narrower than 256 threads are compiled without the masks)
     if (const char *env = getenv("MCL_PHILOX_SHARE_BM")) { int v = atoi(env); pl.share_bm = v < 0 ? 0 : (v > 2 ? 2 : v); }   // knob: 0 off, 1 on, 2 on + self-check
-    if (pl.share_bm) pl.smem += 2 * 4 * (size_t)pl.bm_words;
+    pl.ref_words = (cap_h + 7) / 8;
+    if (nt < 256) pl.share_bm = 0;
+    if (pl.share_bm) pl.smem += 4 * ((size_t)pl.bm_words + (size_t)pl.ref_words);
     return pl;
 }
 
@@ -1156,7 +1185,7 @@ static cudaError_t launch_one(const LaunchParams &p, const RoundKeys &K, const C
 cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_slots*/)
 {
     PhiloxPlan pl = make_plan(p.cap_e, p.cap_h, g_nt_override, p.n_replicas);
-    Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.share_bm, pl.off_holes, pl.off_cand};
+    Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.share_bm, pl.ref_words, pl.off_holes, pl.off_cand};
     RoundKeys K;
     uint64_t s = mix64(p.seed);
     uint32_t k0 = (uint32_t)s, k1 = (uint32_t)(s >> 32);

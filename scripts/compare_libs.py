@@ -21,6 +21,12 @@ def dump(out):
     for tag, wl in (("c2", workloads.c2(n_replicas=8)), ("c5", workloads.c5(n_replicas=200)), ("c2s", workloads.c2(n_replicas=40, n_e=600, n_bins=40)),
                     ("c2two", workloads.c2(n_replicas=6, n_e=5000, physics_overrides=["physics_fp.E_loc_2=1.0", "physics_fp.Retrap=0.3"]))):
         put(tag, engine.run_replicas(wl["replicas"], wl["segments"], wl["max_steps"], seed=5, hist=wl["hist"], trace=True, sync=True))
+    os.environ["MCL_PHILOX_NT"] = "256"            # the production width of 10^4-electron boxes (few replicas would get 512)
+    wl = workloads.c2(n_replicas=6)
+    put("c2nt256", engine.run_replicas(wl["replicas"], wl["segments"], wl["max_steps"], seed=5, hist=wl["hist"], trace=True, sync=True))
+    os.environ["MCL_PHILOX_SHARE_BM"] = "2"       # + self-check of the scan-skip masks (any miss = MCL_ERR_INTERNAL)
+    put("c2nt256v", engine.run_replicas(wl["replicas"], wl["segments"], wl["max_steps"], seed=5, hist=wl["hist"], trace=True, sync=True))
+    del os.environ["MCL_PHILOX_NT"], os.environ["MCL_PHILOX_SHARE_BM"]
     run = initialize_runs(compose(overrides=["exp_type_fp=TLlab", "physics_fp=lab_TL"]))[0]
     for exp in ("tl_clbr", "iso"):
         lt = LabTable(*LAB_CSV[exp], PROJECT_ROOT)
