@@ -1,7 +1,8 @@
 // mcl_philox.cu -- native throughput kernel of the trapped-charge kinetics loop (sm_100a).
 //
-// One CTA (NT = 32..512 threads) per replica; one electron per shared-memory slot, two slots per
-// Philox call.  What one step does (reference src/class/simulate.py:51-92, tl_trap_lab.py:90-108):
+// One CTA (NT = 32..512 threads) per replica; one electron per shared-memory slot; one Philox call serves a chunk of
+// four slots when the two tunnelling channels are identical (no selector needed), two slots otherwise.
+// What one step does (reference src/class/simulate.py:51-92, tl_trap_lab.py:90-108):
 //   1. SWEEP.  Every alive electron i draws a selector and an exponential and forms its waiting time
 //        wait_i = E_i / (k_cb + b*exp(-E_loc/kT - alpha*r_i))          (engine.py:65-77, tl_trap_lab.py:51)
 //      in the log2 domain:  l_i = lg2(-lg2 u_i) - lg2 k_i,  wait_i = ln2 * 2^l_i,
@@ -13,7 +14,8 @@
 //      (value, slot, its hole), double-buffered by step parity -> ONE __syncthreads -> every warp
 //      re-reduces the <= 16 rows and derives the same decision from uniform inputs.
 //   3. EVENT.  dt = min(dt_fill, dt_recomb, dt_cap).  Recombination (engine.py:154-175): the owner
-//      tombstones the slot; every thread scans the near[] entries of its own chunks for the dead hole; a hit
+//      tombstones the slot; every thread scans the near[] entries of its own chunks for the dead hole (wide CTAs
+//      keep per-hole masks that tell whether anybody, and which warp group, can have a hit at all); a hit
 //      is re-targeted by its owner from the electron's K nearest-hole candidate list (exact while no hole
 //      was ever added), else by a grid search of the owner's warp.  No CTA barrier.  Fill
 //      (engine.py:133-152, stale-cache semantics): warp 0 places the pair; one extra barrier.
@@ -23,7 +25,7 @@
 // cell grid; one warp per occupied cell loads the ~95 surrounding holes into registers once and builds the
 // K-nearest lists of the cell's electrons.
 // Random numbers: Philox4x32-10, key = seed (launch-wide round keys live in the constant bank),
-// counter = (slot pair | element index, step, replica id lo, replica id hi | domain).  Results
+// counter = (chunk or slot pair | element index, step, replica id lo, replica id hi | domain).  Results
 // depend only on (seed, global replica id), never on the launch shape or the GPU count.
 //
 // Electron state: cr[slot] = alpha*log2(e)*r (FP32, +inf = empty slot), near[slot] = hole slot, both in
