@@ -62,7 +62,7 @@ struct RoundKeys { uint32_t k[20]; };
 #ifdef MCL_PROFILE_SKEW
 // Profiling build only (scripts/build_variant.sh skew -DMCL_PROFILE_SKEW; scripts/skew_probe.py): cycles per warp index
 // spent in the sweep / waiting at the step barrier / between the barrier and the next sweep, and the step count.
-__device__ unsigned long long g_prof[4][32];
+__device__ unsigned long long g_prof[10][32];      // rows 4..9: parts of the time after the barrier (see the marks)
 #endif
 
 struct Cfg {
@@ -412,7 +412,10 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     NearT *cand_j = reinterpret_cast<NearT *>(cand_d + ce);           // [cap_e][KC] their slots (NEAR_DEAD = none)
 
 #ifdef MCL_PROFILE_SKEW
-    long long pf_sweep = 0, pf_wait = 0, pf_rest = 0, pf_steps = 0, pf_t = 0;
+    long long pf_sweep = 0, pf_wait = 0, pf_rest = 0, pf_steps = 0, pf_t = 0, pf_m = 0, pf_part[6] = {0, 0, 0, 0, 0, 0};
+#define MCL_MARK(i) { const long long now_ = clock64(); pf_part[i] += now_ - pf_m; pf_m = now_; }
+#else
+#define MCL_MARK(i)
 #endif
     int status = MCL_OK;
     const float core_s = (float)(rp.side * rp.alpha * L2E);
@@ -765,7 +768,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
 #endif
             cta_sync<NT>();                                   // ===== B1
 #ifdef MCL_PROFILE_SKEW
-            { const long long now = clock64(); pf_wait += now - pf_t; pf_t = now; pf_steps++; }
+            { const long long now = clock64(); pf_wait += now - pf_t; pf_t = now; pf_steps++; pf_m = now; }
 #endif
             float vmin; int smin, hmin;
             {
@@ -803,6 +806,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             const int n_before = n_e;
             const double t_new = t_cur + (double)dt;
 
+            MCL_MARK(0)      // reduce + decision
             // ---------------- fused occupancy histogram: edges passed while n_e was n_before
             if (hedge_next <= t_new) {
                 // hbin_next <= n_bins; edge n_bins (the right end of the axis) closes the last bin
@@ -818,6 +822,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             }
             t_cur = t_new;
 
+            MCL_MARK(1)      // histogram
             int ev = 0;
             if (is_rec) {
                 // ---------------- Box.remove_pair (engine.py:154-175)
@@ -941,7 +946,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         }
                     }
                 };
+                MCL_MARK(2)  // retire the pair
                 if (!lone || verify_skip) { if (h2 >= 0) scan(std::true_type{}); else scan(std::false_type{}); }
+                MCL_MARK(3)  // scan + re-target from the lists
                 // Exhausted lists and fill mode (new holes become visible on a re-search, engine.py:171-175):
                 // the owner's WARP searches the cell grid cooperatively; still no CTA barrier.
                 {
@@ -963,6 +970,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         need |= __ballot_sync(0xffffffffu, lane == src && redo >= 0) ;
                     }
                 }
+                MCL_MARK(4)  // warp searches
                 // ---------------- compaction: keep tombstones below 1/TOMB_DIV of the slots in use.  The Philox counter of a
                 // clock is its slot, so WHEN slots move is part of the stream definition: TOMB_DIV is one constant for
                 // every CTA width (results must not depend on the launch shape).
@@ -1066,6 +1074,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 cta_sync<NT>();
             }
 
+            MCL_MARK(5)      // compaction / fill
             // ---------------- record (simulate.py:64,85-89): staged, flushed 32 at a time
             if (trace && tid == 0) { rec_ev[rec_i & 31] = ev; rec_ne[rec_i & 31] = n_e; rec_t[rec_i & 31] = t_off + t_cur; }
             rec_i++;
@@ -1085,6 +1094,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     if (lane == 0) {
         atomicAdd(&g_prof[0][warp], (unsigned long long)pf_sweep); atomicAdd(&g_prof[1][warp], (unsigned long long)pf_wait);
         atomicAdd(&g_prof[2][warp], (unsigned long long)pf_rest); atomicAdd(&g_prof[3][warp], (unsigned long long)pf_steps);
+        for (int i = 0; i < 6; i++) atomicAdd(&g_prof[4 + i][warp], (unsigned long long)pf_part[i]);
     }
 #endif
     flush_records(rec_i & 31);
@@ -1117,8 +1127,8 @@ int philox_max_slots() { return 24000; }
 extern "C" int mcl_debug_prof(unsigned long long *out, int reset)
 {
     cudaDeviceSynchronize();
-    cudaError_t e = cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 4 * 32);
-    if (reset) { static unsigned long long z[4 * 32]; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 10 * 32);
+    if (reset) { static unsigned long long z[10 * 32]; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
     return (int)e;
 }
 #endif
