@@ -134,12 +134,19 @@ __device__ unsigned long long warp_nearest(const Holes &H, float x, float y, flo
             if ((unsigned)ax >= (unsigned)G || (unsigned)ay >= (unsigned)G || (unsigned)az >= (unsigned)G) continue;
             int c = (ax * G + ay) * G + az;
             int j0 = H.cell_start[c], j1 = H.cell_start[c + 1];
-            for (int j = j0; j < j1; j++) {
-                const float4 hp = H.pos[j];
-                float dx = x - hp.x, dy = y - hp.y, dz = z - hp.z;
-                float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
-                best = (key < best && j != exclude) ? key : best;
+            // four holes of the cell per round trip to L2 / HBM (a cell holds ~3.5): the loads are what a search costs
+            for (int jb = j0; jb < j1; jb += 4) {
+                float4 hp[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) hp[u] = H.pos[min(jb + u, j1 - 1)];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int j = jb + u;
+                    float dx = x - hp[u].x, dy = y - hp[u].y, dz = z - hp[u].z;
+                    float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                    unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
+                    best = (j < j1 && key < best && j != exclude) ? key : best;
+                }
             }
         }
         best = warp_min_u64(best);
@@ -155,13 +162,19 @@ __device__ unsigned long long warp_nearest(const Holes &H, float x, float y, flo
         float d2b = __uint_as_float((uint32_t)(best >> 32));
         if (covered || d2b <= bound * bound) break;
     }
-    // holes added by fills live outside the grid
-    for (int j = H.n_h0 + lane; j < H.n_slots; j += 32) {
-        const float4 hp = H.pos[j];
-        float dx = x - hp.x, dy = y - hp.y, dz = z - hp.z;
-        float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
-        best = (key < best && j != exclude) ? key : best;
+    // holes added by fills live outside the grid (again four loads in flight per lane)
+    for (int jb = H.n_h0 + lane; jb < H.n_slots; jb += 128) {
+        float4 hp[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) hp[u] = H.pos[min(jb + 32 * u, H.n_slots - 1)];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int j = jb + 32 * u;
+            float dx = x - hp[u].x, dy = y - hp[u].y, dz = z - hp[u].z;
+            float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
+            best = (j < H.n_slots && key < best && j != exclude) ? key : best;
+        }
     }
     return warp_min_u64(best);
 }
