@@ -160,6 +160,9 @@ __device__ unsigned long long warp_nearest(const Holes &H, float x, float y, flo
         if (cz - R > 0) { bound = fminf(bound, z - (cz - R) * H.w); covered = false; }
         if (cz + R < G - 1) { bound = fminf(bound, (cz + R + 1) * H.w - z); covered = false; }
         float d2b = __uint_as_float((uint32_t)(best >> 32));
+#ifdef MCL_PROFILE_SKEW
+        if (lane == 0) atomicAdd(&g_prof[9][min(R, 31)], 1ull);       // searches that scanned ring R
+#endif
         if (covered || d2b <= bound * bound) break;
     }
     // holes added by fills live outside the grid (again four loads in flight per lane)
@@ -1107,7 +1110,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     if (lane == 0) {
         atomicAdd(&g_prof[0][warp], (unsigned long long)pf_sweep); atomicAdd(&g_prof[1][warp], (unsigned long long)pf_wait);
         atomicAdd(&g_prof[2][warp], (unsigned long long)pf_rest); atomicAdd(&g_prof[3][warp], (unsigned long long)pf_steps);
-        for (int i = 0; i < 6; i++) atomicAdd(&g_prof[4 + i][warp], (unsigned long long)pf_part[i]);
+        for (int i = 0; i < 5; i++) atomicAdd(&g_prof[4 + i][warp], (unsigned long long)pf_part[i]);
     }
 #endif
     flush_records(rec_i & 31);

@@ -19,5 +19,6 @@ for w in range(nw):
     tot = a[0, w] + a[1, w] + a[2, w]
     print(f"warp {w}: per step cycles sweep {a[0, w] / a[3, w]:8.0f}  wait {a[1, w] / a[3, w]:8.0f}  rest {a[2, w] / a[3, w]:8.0f}   "
           f"shares {a[0, w] / tot:.3f} {a[1, w] / tot:.3f} {a[2, w] / tot:.3f}")
-names = ["reduce+decision", "histogram", "retire pair", "scan+lists", "warp searches", "compaction/fill"]
+names = ["reduce+decision", "histogram", "retire pair", "scan+lists", "warp searches"]
+print("grid searches that scanned ring R = 1, 2, ...:", [int(v) for v in a[9, 1:9]], "in", int(a[3, 0]), "replica-steps")
 print("after the barrier, cycles per step (mean over warps): " + ", ".join(f"{n} {a[4 + i, :nw].sum() / a[3, :nw].sum():.0f}" for i, n in enumerate(names)))
