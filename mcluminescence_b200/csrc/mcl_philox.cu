@@ -50,6 +50,9 @@ constexpr uint32_t DOM_STEP = 0u, DOM_SCALAR = 1u, DOM_SEED_E = 2u, DOM_SEED_H =
 #ifndef MCL_SCAN_UNROLL_NARROW
 #define MCL_SCAN_UNROLL_NARROW 1
 #endif
+#ifndef MCL_FAST_LOOP
+#define MCL_FAST_LOOP 1
+#endif
 #ifndef MCL_ONE_CHAINS
 #define MCL_ONE_CHAINS 2
 #endif
@@ -74,6 +77,7 @@ struct Cfg {
     int ref_words;     // smem words of the warp-group reference mask (4 bits per hole)
     size_t off_holes;  // byte offset of the hole table inside the slab (16-byte aligned)
     size_t off_cand;   // byte offset of the candidate lists inside the slab
+    int fast;          // 1: legs that qualify run the specialised step loop (0: always the general one; same results)
 };
 
 __device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
@@ -664,445 +668,466 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         };
         set_T(0.0);
 
-        for (;;) {
-            // ---------------- loop condition (simulate.py:51; tl_trap_lab.py:90,147)
-            if (!lab) { if (!(t_cur <= S.duration)) break; }
-            else if (iso) { if (!(obs_idx < rp.obs_count)) break; }
-            else { if (!(t_cur < S.duration)) break; }
-            if (rec_i >= p.max_steps) { status = MCL_ERR_STEPS; break; }
+        // The step loop exists twice.  FAST: the simulate protocol without a dose, without per-step records and while no
+        // hole was ever added -- what BASELINE-sized ensembles run; protocol, dose, trace and fill-mode branches are compiled
+        // out, which shortens the serial part of a step (C2 +6.7 %, C5 +9.3 %).  The general loop takes over, repeating the
+        // step in hand, the moment the filling clock could matter.  Same records either way (scripts/compare_libs.py).
+        auto step_loop = [&](auto fast_tag) -> bool {         // true: leg finished (or error), false: continue in the general loop
+            constexpr bool FAST = decltype(fast_tag)::value;
+            const bool lab_o = lab, iso_o = iso, trace_o = trace, dose_o = dose_on, verify_o = verify_skip;
+            if (FAST) __builtin_assume(!ever_filled);
+            {
+            const bool lab = FAST ? false : lab_o, iso = FAST ? false : iso_o, trace = FAST ? false : trace_o;
+            const bool dose_on = FAST ? false : dose_o, verify_skip = FAST ? false : verify_o;
+            for (;;) {
+                // ---------------- loop condition (simulate.py:51; tl_trap_lab.py:90,147)
+                if (!lab) { if (!(t_cur <= S.duration)) break; }
+                else if (iso) { if (!(obs_idx < rp.obs_count)) break; }
+                else { if (!(t_cur < S.duration)) break; }
+                if (rec_i >= p.max_steps) { status = MCL_ERR_STEPS; break; }
 
-            // ---------------- temperature-dependent scalars (uniform; FP32 from an FP64 clock)
-            if (!T_const) set_T(t_cur);
-            const int par = rec_i & 1;
+                // ---------------- temperature-dependent scalars (uniform; FP32 from an FP64 clock)
+                if (!T_const) set_T(t_cur);
+                const int par = rec_i & 1;
 
 #ifdef MCL_PROFILE_SKEW
-            { const long long now = clock64(); if (pf_t) pf_rest += now - pf_t; pf_t = now; }
+                { const long long now = clock64(); if (pf_t) pf_rest += now - pf_t; pf_t = now; }
 #endif
-            // ---------------- per-electron clocks + running argmin
-            float best = F_INF; int bslot = -1;
-            // A thread owns whole CHUNKS of SPC = 4 slots (chunk b = slots 4b.. belongs to thread b % NT): one 16-byte
-            // load feeds the clocks of a chunk and the post-event scan reads its nearest-hole slots with one load.
-            const int n_chunks = (n_slots + SPC - 1) / SPC;
-            auto pair_loop = [&](auto with_cb, auto one_channel) {
-                constexpr bool CB = decltype(with_cb)::value;
-                constexpr bool ONE = decltype(one_channel)::value;     // both tunnelling channels identical
-                if constexpr (ONE) {
-                    // Identical channels: the selector draw cannot change anything, so no word is spent on it.  One
-                    // Philox call serves the FOUR slots of a chunk (word k -> slot 4b + k); MCL_ONE_CHAINS chunks of
-                    // the same owner per iteration keep that many independent Philox chains in flight.
-                    const float4 *cr4 = reinterpret_cast<const float4 *>(cr);
-                    auto chunks = [&](auto n_chains, int b0) {
-                        constexpr int NCH = decltype(n_chains)::value;
-                        float cs[NCH][4];
-                        uint32_t w[NCH][4];
+                // ---------------- per-electron clocks + running argmin
+                float best = F_INF; int bslot = -1;
+                // A thread owns whole CHUNKS of SPC = 4 slots (chunk b = slots 4b.. belongs to thread b % NT): one 16-byte
+                // load feeds the clocks of a chunk and the post-event scan reads its nearest-hole slots with one load.
+                const int n_chunks = (n_slots + SPC - 1) / SPC;
+                auto pair_loop = [&](auto with_cb, auto one_channel) {
+                    constexpr bool CB = decltype(with_cb)::value;
+                    constexpr bool ONE = decltype(one_channel)::value;     // both tunnelling channels identical
+                    if constexpr (ONE) {
+                        // Identical channels: the selector draw cannot change anything, so no word is spent on it.  One
+                        // Philox call serves the FOUR slots of a chunk (word k -> slot 4b + k); MCL_ONE_CHAINS chunks of
+                        // the same owner per iteration keep that many independent Philox chains in flight.
+                        const float4 *cr4 = reinterpret_cast<const float4 *>(cr);
+                        auto chunks = [&](auto n_chains, int b0) {
+                            constexpr int NCH = decltype(n_chains)::value;
+                            float cs[NCH][4];
+                            uint32_t w[NCH][4];
 #pragma unroll
-                        for (int q = 0; q < NCH; q++) {
-                            const int b = b0 + q * NT;
-                            const float4 cq = cr4[b];
-                            cs[q][0] = cq.x; cs[q][1] = cq.y; cs[q][2] = cq.z; cs[q][3] = cq.w;
-                            w[q][0] = (uint32_t)b; w[q][1] = (uint32_t)rec_i; w[q][2] = rid_lo; w[q][3] = rid_hi | (DOM_STEP1 << 28);
-                        }
+                            for (int q = 0; q < NCH; q++) {
+                                const int b = b0 + q * NT;
+                                const float4 cq = cr4[b];
+                                cs[q][0] = cq.x; cs[q][1] = cq.y; cs[q][2] = cq.z; cs[q][3] = cq.w;
+                                w[q][0] = (uint32_t)b; w[q][1] = (uint32_t)rec_i; w[q][2] = rid_lo; w[q][3] = rid_hi | (DOM_STEP1 << 28);
+                            }
 #pragma unroll
-                        for (int q = 0; q < NCH; q++) philox4x32_10(w[q][0], w[q][1], w[q][2], w[q][3], K);
+                            for (int q = 0; q < NCH; q++) philox4x32_10(w[q][0], w[q][1], w[q][2], w[q][3], K);
 #pragma unroll
-                        for (int q = 0; q < NCH; q++) {
+                            for (int q = 0; q < NCH; q++) {
 #pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                const float le = lg2_fast(-lg2_fast(u01(w[q][k])));
-                                float l;
-                                if (CB) {
-                                    // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
-                                    const float a = A1 - cs[q][k];
-                                    const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
-                                    l = (le - kk) + (cs[q][k] - cs[q][k]);
-                                } else {
-                                    l = le + cs[q][k];              // the uniform prefactor A1 is subtracted after the loop
+                                for (int k = 0; k < 4; k++) {
+                                    const float le = lg2_fast(-lg2_fast(u01(w[q][k])));
+                                    float l;
+                                    if (CB) {
+                                        // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
+                                        const float a = A1 - cs[q][k];
+                                        const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
+                                        l = (le - kk) + (cs[q][k] - cs[q][k]);
+                                    } else {
+                                        l = le + cs[q][k];              // the uniform prefactor A1 is subtracted after the loop
+                                    }
+                                    if (l < best) { best = l; bslot = 4 * (b0 + q * NT) + k; }
                                 }
-                                if (l < best) { best = l; bslot = 4 * (b0 + q * NT) + k; }
+                            }
+                        };
+                        int b0 = tid;
+                        for (; b0 + (MCL_ONE_CHAINS - 1) * NT < n_chunks; b0 += MCL_ONE_CHAINS * NT)
+                            chunks(std::integral_constant<int, MCL_ONE_CHAINS>{}, b0);
+                        for (; b0 < n_chunks; b0 += NT) chunks(std::integral_constant<int, 1>{}, b0);       // tail: no wasted calls
+                        if (!CB) best -= A1;
+                    } else {
+                        for (int b = tid; b < n_chunks; b += NT) {
+                            float cs[SPC];
+                            const float4 cq = reinterpret_cast<const float4 *>(cr)[b];
+                            cs[0] = cq.x; cs[1] = cq.y; cs[2] = cq.z; cs[3] = cq.w;
+                            float l[SPC];
+#pragma unroll
+                            for (int i = 0; i < PPC; i++) {
+                                uint32_t c0 = (uint32_t)(PPC * b + i), c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);
+                                philox4x32_10(c0, c1, c2, c3, K);
+                                // the selector draws (c0, c2) pick the channel
+                                const float a0 = ((c0 < thr) ? A2 : A1) - cs[2 * i];
+                                const float a1 = ((c2 < thr) ? A2 : A1) - cs[2 * i + 1];
+                                const float le0 = lg2_fast(-lg2_fast(u01(c1)));
+                                const float le1 = lg2_fast(-lg2_fast(u01(c3)));
+                                if (CB) {
+                                    const float k0 = fmaxf(a0, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a0 - g)));
+                                    const float k1 = fmaxf(a1, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a1 - g)));
+                                    l[2 * i] = (le0 - k0) + (cs[2 * i] - cs[2 * i]);
+                                    l[2 * i + 1] = (le1 - k1) + (cs[2 * i + 1] - cs[2 * i + 1]);
+                                } else {
+                                    l[2 * i] = le0 - a0;
+                                    l[2 * i + 1] = le1 - a1;
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < SPC; i++) if (l[i] < best) { best = l[i]; bslot = SPC * b + i; }
+                        }
+                    }
+                };
+                if (A1 == A2) { if (has_cb) pair_loop(std::true_type{}, std::true_type{}); else pair_loop(std::false_type{}, std::true_type{}); }
+                else          { if (has_cb) pair_loop(std::true_type{}, std::false_type{}); else pair_loop(std::false_type{}, std::false_type{}); }
+                // warp argmin -> one row per warp
+                {
+                    float wv = warp_min_f32(best);
+                    unsigned m = __ballot_sync(0xffffffffu, best == wv);
+                    int src = m ? (__ffs(m) - 1) : 0;
+                    int ws_ = __shfl_sync(0xffffffffu, bslot, src);
+                    __syncwarp();
+                    if (lane == 0) red_row[par][warp] = make_int4(__float_as_int(wv), ws_, ws_ >= 0 ? (int)near[ws_] : -1, 0);
+                }
+                if (warp == 0 && ((rec_i & 31) == 0 || !draws_valid)) {
+                    // step scalars (fill clock + coordinates of a would-be new electron) of the 32 steps of this block
+                    // of records, one Philox call per lane: counter-based, so step k gets the same words as if it were
+                    // drawn on its own.  Double-buffered: the other buffer may still be read by a warp that is late in
+                    // the previous step.
+                    uint32_t c0 = 0u, c1 = (uint32_t)((rec_i & ~31) + lane), c2 = rid_lo, c3 = rid_hi | (DOM_SCALAR << 28);
+                    philox4x32_10(c0, c1, c2, c3, K);
+                    uint32_t *d = stepdraw[(rec_i >> 5) & 1][lane];
+                    d[0] = c0; d[1] = c1; d[2] = c2; d[3] = c3;
+                }
+                draws_valid = true;
+#ifdef MCL_PROFILE_SKEW
+                { const long long now = clock64(); pf_sweep += now - pf_t; pf_t = now; }
+#endif
+                cta_sync<NT>();                                   // ===== B1
+#ifdef MCL_PROFILE_SKEW
+                { const long long now = clock64(); pf_wait += now - pf_t; pf_t = now; pf_steps++; pf_m = now; }
+#endif
+                float vmin; int smin, hmin;
+                {
+                    const int4 row = lane < NW ? red_row[par][lane] : make_int4(__float_as_int(F_INF), -1, -1, 0);
+                    const float v = __int_as_float(row.x);
+                    const int s = row.y, hh = row.z;
+                    vmin = warp_min_f32(v);
+                    unsigned m = __ballot_sync(0xffffffffu, v == vmin);
+                    const int src = m ? (__ffs(m) - 1) : 0;
+                    smin = __shfl_sync(0xffffffffu, s, src);
+                    hmin = __shfl_sync(0xffffffffu, hh, src);
+                }
+                // ---------------- filling clock (tl_trap_lab.py:53-60) and dt (simulate.py:58-60)
+                // Without a dose the clock is exponential(1e20 s) >= -ln(1 - 2^-24) * 1e20 = 5.96e12 s: it can only matter (the
+                // reference's spurious fill) when nothing else happens before 5e12 s -- otherwise it is not evaluated.
+                const float dt_rec0 = n_e > 0 ? ex2_fast(vmin) * LN2F : F_INF;
+                float dt_fill = F_INF;
+                if (FAST && !(fminf(dt_rec0, dt_cap) < 5.0e12f)) {
+                    // the filling clock could matter (spurious fill): the general loop repeats this step
+                    cta_sync<NT>();
+                    return false;
+                }
+                if (dose_on || !((lab ? dt_rec0 : fminf(dt_rec0, dt_cap)) < 5.0e12f)) {       // (the lab loops have no step cap)
+                    float lam = (n_e == rp.N_e || !dose_on) ? 1e-20f : dose_over_D0 * (float)(rp.N_e - n_e);
+                    dt_fill = lam > 0.0f ? __fdividef(-lg2_fast(u01(stepdraw[(rec_i >> 5) & 1][rec_i & 31][0])) * LN2F, lam) : 1e20f;
+                }
+                const float dt_rec = n_e > 0 ? dt_rec0 : dt_fill;
+                float dt; bool is_fill, is_rec;
+                if (!lab) {
+                    dt = fminf(fminf(dt_fill, dt_rec), dt_cap);
+                    is_fill = FAST ? false : (dt == dt_fill);
+                    is_rec = !is_fill && (dt == dt_rec);
+                } else {
+                    is_fill = (dt_fill <= dt_rec);
+                    is_rec = !is_fill;
+                    dt = is_fill ? dt_fill : dt_rec;
+                }
+                es32 += (uint32_t)n_e;
+                if (es32 > 0xC0000000u) { esteps += es32; es32 = 0u; }      // the 64-bit total lives in local memory
+                const int n_before = n_e;
+                const double t_new = t_cur + (double)dt;
+
+                MCL_MARK(0)      // reduce + decision
+                // ---------------- fused occupancy histogram: edges passed while n_e was n_before
+                if (hedge_next <= t_new) {
+                    // hbin_next <= n_bins; edge n_bins (the right end of the axis) closes the last bin
+                    while (hedge_next <= t_new) {
+                        if (tid == 0 && p.hist_occ && hbin_next < p.hist.n_bins) {
+                            size_t q = (size_t)hrow * p.hist.n_bins + hbin_next;
+                            atomicAdd(&p.hist_occ[q], (unsigned long long)n_before);
+                            if (p.hist_occ_sq) atomicAdd(&p.hist_occ_sq[q], (unsigned long long)n_before * (unsigned long long)n_before);
+                        }
+                        hbin_next++;
+                        hedge_next = hbin_next <= p.hist.n_bins ? edge_after(hbin_next, hedge_next) : CUDART_INF;
+                    }
+                }
+                t_cur = t_new;
+
+                MCL_MARK(1)      // histogram
+                int ev = 0;
+                if (is_rec) {
+                    // ---------------- Box.remove_pair (engine.py:154-175)
+                    ev = 1;
+                    const int h = hmin;                                    // nearest hole of the winner (read before B1)
+                    if (tid == ((smin / SPC) % NT)) { cr[smin] = F_INF; near[smin] = (NearT)NEAR_DEAD; }   // owner tombstones it
+                    n_e--;
+                    int h2 = -1;
+                    if (ever_filled) {
+                        // stale-cache mode: the reference also refreshes electrons cached on the hole that
+                        // FOLLOWS the removed one in index order (shift-then-mask, engine.py:168-171)
+                        const int last_w = (H.n_slots - 1) >> 5;
+                        int w_ = (h + 1) >> 5;
+                        uint32_t bits = w_ <= last_w ? (hole_bm[w_] & (0xffffffffu << ((h + 1) & 31))) : 0u;
+                        while (!bits && w_ < last_w) bits = hole_bm[++w_];
+                        if (bits) { const int j = 32 * w_ + __ffs(bits) - 1; if (j < H.n_slots) h2 = j; }
+                    }
+                    if (tid == 0) {
+                        hpos[h].x = DEAD_X;
+                        // Bit h is the only bit of the bitmap that changes in this phase, and every concurrent reader
+                        // (retarget below, other warps) skips hole h before it looks at a word: reading the old or the
+                        // new word gives the same answer.  compute-sanitizer racecheck flags exactly this read / RMW
+                        // overlap; it is benign by construction.  The next barrier publishes the bit.
+                        hole_bm[h >> 5] &= ~(1u << (h & 31));
+                        if (hist_on && p.hist_events) {
+                            // edges up to t_cur have been passed: the event sits in the bin before the cursor
+                            const int b = h_mono ? (hbin_next - 1) : bin_of(t_cur);
+                            if (b >= 0 && b < p.hist.n_bins) atomicAdd(&p.hist_events[(size_t)hrow * p.hist.n_bins + b], 1ull);
+                        }
+                    }
+                    if (h >= n_h0) n_fill_alive--;
+                    // Which of MY other electrons were cached on h (or h2)?  A thread owns the pairs it sweeps
+                    // (q = tid, tid + NT, ...), and only the owner ever touches cr[] / near[] of a pair outside
+                    // barrier-protected phases -- so re-targeting needs no CTA barrier at all.
+                    // no other electron can be cached on h if h was never the target of a second one
+                    const bool lone = share_bm && !ever_filled &&
+                                      (!((multi_bm[h >> 5] >> (h & 31)) & 1u) ||                    // nobody else at all, or
+                                       !((ref4[h >> 3] >> (4 * (h & 7) + my_group)) & 1u));         // nobody in MY warp group (warp-uniform)
+                    int redo = -1;                      // a slot of mine that needs the warp-cooperative search
+                    auto retarget = [&](int sl) {
+                        bool fixed = false;
+                        if (!ever_filled) {
+                            // no hole was ever added: the new nearest is the first remembered candidate that is
+                            // still alive (and is not the hole dying now, whose bitmap bit may not be visible yet)
+                            // distances and slots of the list are fetched together: ONE round trip to L2 / HBM
+                            const float4 d4 = cand_d[sl];
+                            uint32_t cj[KC];
+                            if (sizeof(NearT) == 2) {
+                                const uint2 v = *reinterpret_cast<const uint2 *>(cand_j + (size_t)sl * KC);
+                                cj[0] = v.x & 0xffffu; cj[1] = v.x >> 16; cj[2] = v.y & 0xffffu; cj[3] = v.y >> 16;
+                            } else {
+                                const uint4 v = *reinterpret_cast<const uint4 *>(cand_j + (size_t)sl * KC);
+                                cj[0] = v.x; cj[1] = v.y; cj[2] = v.z; cj[3] = v.w;
+                            }
+                            const float dk[KC] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                            for (int c = 0; c < KC; c++) {
+                                const uint32_t j = cj[c];
+                                if (!fixed && j != NEAR_DEAD && j != (uint32_t)h && ((hole_bm[j >> 5] >> (j & 31)) & 1u)) {
+                                    cr[sl] = dk[c]; near[sl] = (NearT)j; fixed = true;
+                                    if (share_bm) mark_target(j, sl);
+                                }
+                            }
+                        }
+                        return fixed;
+                    };
+                    auto scan = [&](auto two_targets) {
+                        constexpr bool TWO = decltype(two_targets)::value;
+                        constexpr int NWORD = SPC * (int)sizeof(NearT) / 4;       // 32-bit words of near[] per chunk
+                        // chunks whose loads are in flight together (narrow CTAs: few chunks per thread, and their 16 CTAs per SM
+                        // at different phases feel every extra kilobyte of code in the instruction cache)
+                        constexpr int SU = NT >= 256 ? MCL_SCAN_UNROLL : MCL_SCAN_UNROLL_NARROW;
+                        const uint32_t hh = (uint32_t)h * 0x00010001u, hh2 = (uint32_t)h2 * 0x00010001u;
+                        for (int b0 = tid; b0 < n_chunks; b0 += SU * NT) {
+                            uint32_t w[SU][NWORD];
+#pragma unroll
+                            for (int u = 0; u < SU; u++) {
+                                const int b = b0 + u * NT;
+                                if (u > 0 && b >= n_chunks) {             // past the end: the empty-slot pattern matches no hole
+#pragma unroll
+                                    for (int k = 0; k < NWORD; k++) w[u][k] = 0xffffffffu;
+                                } else if (NWORD == 4) {
+                                    const uint4 v = reinterpret_cast<const uint4 *>(near)[b];
+                                    w[u][0] = v.x; w[u][1 % NWORD] = v.y; w[u][2 % NWORD] = v.z; w[u][3 % NWORD] = v.w;
+                                } else {
+                                    const uint2 v = reinterpret_cast<const uint2 *>(near)[b];
+                                    w[u][0] = v.x; w[u][1 % NWORD] = v.y;
+                                }
+                            }
+                            uint32_t hits = 0u;                           // bit u: chunk b0 + u * NT may hold a match
+#pragma unroll
+                            for (int u = 0; u < SU; u++) {
+                                bool hit;
+                                if (sizeof(NearT) == 2) {
+                                    // 16-bit slots: zero-halfword test (false positives possible, re-checked below)
+                                    auto zh = [](uint32_t t) { return (t - 0x00010001u) & ~t & 0x80008000u; };
+                                    uint32_t z = 0u;
+#pragma unroll
+                                    for (int k = 0; k < NWORD; k++) { z |= zh(w[u][k] ^ hh); if (TWO) z |= zh(w[u][k] ^ hh2); }
+                                    hit = z != 0u;
+                                } else {
+                                    hit = false;
+#pragma unroll
+                                    for (int k = 0; k < NWORD; k++) { hit |= (w[u][k] == (uint32_t)h); if (TWO) hit |= (w[u][k] == (uint32_t)h2); }
+                                }
+                                hits |= hit ? (1u << u) : 0u;
+                            }
+                            while (hits) {
+                                const int b = b0 + (__ffs(hits) - 1) * NT;
+                                hits &= hits - 1u;
+                                for (int k = 0; k < SPC; k++) {
+                                    const int sl = SPC * b + k;
+                                    const uint32_t nn = near[sl];
+                                    if ((nn == (uint32_t)h || (TWO && nn == (uint32_t)h2)) && sl != smin && lone) atomicOr(&s_err, 1);
+                                    if ((nn == (uint32_t)h || (TWO && nn == (uint32_t)h2)) && sl != smin && !retarget(sl)) {
+                                        // rare: park it until the warp search below
+                                        if (redo >= 0) cr[sl] = -1.0f;      // more than one: mark, found again below
+                                        else redo = sl;
+                                    }
+                                }
                             }
                         }
                     };
-                    int b0 = tid;
-                    for (; b0 + (MCL_ONE_CHAINS - 1) * NT < n_chunks; b0 += MCL_ONE_CHAINS * NT)
-                        chunks(std::integral_constant<int, MCL_ONE_CHAINS>{}, b0);
-                    for (; b0 < n_chunks; b0 += NT) chunks(std::integral_constant<int, 1>{}, b0);       // tail: no wasted calls
-                    if (!CB) best -= A1;
-                } else {
-                    for (int b = tid; b < n_chunks; b += NT) {
-                        float cs[SPC];
-                        const float4 cq = reinterpret_cast<const float4 *>(cr)[b];
-                        cs[0] = cq.x; cs[1] = cq.y; cs[2] = cq.z; cs[3] = cq.w;
-                        float l[SPC];
-#pragma unroll
-                        for (int i = 0; i < PPC; i++) {
-                            uint32_t c0 = (uint32_t)(PPC * b + i), c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);
-                            philox4x32_10(c0, c1, c2, c3, K);
-                            // the selector draws (c0, c2) pick the channel
-                            const float a0 = ((c0 < thr) ? A2 : A1) - cs[2 * i];
-                            const float a1 = ((c2 < thr) ? A2 : A1) - cs[2 * i + 1];
-                            const float le0 = lg2_fast(-lg2_fast(u01(c1)));
-                            const float le1 = lg2_fast(-lg2_fast(u01(c3)));
-                            if (CB) {
-                                const float k0 = fmaxf(a0, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a0 - g)));
-                                const float k1 = fmaxf(a1, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a1 - g)));
-                                l[2 * i] = (le0 - k0) + (cs[2 * i] - cs[2 * i]);
-                                l[2 * i + 1] = (le1 - k1) + (cs[2 * i + 1] - cs[2 * i + 1]);
-                            } else {
-                                l[2 * i] = le0 - a0;
-                                l[2 * i + 1] = le1 - a1;
+                    MCL_MARK(2)  // retire the pair
+                    if (!lone || verify_skip) { if (h2 >= 0) scan(std::true_type{}); else scan(std::false_type{}); }
+                    MCL_MARK(3)  // scan + re-target from the lists
+                    // Exhausted lists and fill mode (new holes become visible on a re-search, engine.py:171-175):
+                    // the owner's WARP searches the cell grid cooperatively; still no CTA barrier.
+                    {
+                        unsigned need = __ballot_sync(0xffffffffu, redo >= 0);
+                        while (need) {
+                            const int src = __ffs(need) - 1;
+                            need &= need - 1;
+                            const int sl = __shfl_sync(0xffffffffu, redo, src);
+                            unsigned long long b = warp_nearest(H, ex[sl], ey[sl], ez[sl], lane, h);
+                            if (lane == src) {
+                                cr[sl] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[sl] = (NearT)(uint32_t)b;
+                                if (share_bm && !ever_filled) mark_target((uint32_t)b, sl);
+                                // further parked slots of this lane were marked with cr = -1
+                                redo = -1;
+                                for (int b = tid; b < n_chunks && redo < 0; b += NT)
+                                    for (int k = 0; k < SPC && redo < 0; k++)
+                                        if (cr[SPC * b + k] == -1.0f) redo = SPC * b + k;
                             }
-                        }
-#pragma unroll
-                        for (int i = 0; i < SPC; i++) if (l[i] < best) { best = l[i]; bslot = SPC * b + i; }
-                    }
-                }
-            };
-            if (A1 == A2) { if (has_cb) pair_loop(std::true_type{}, std::true_type{}); else pair_loop(std::false_type{}, std::true_type{}); }
-            else          { if (has_cb) pair_loop(std::true_type{}, std::false_type{}); else pair_loop(std::false_type{}, std::false_type{}); }
-            // warp argmin -> one row per warp
-            {
-                float wv = warp_min_f32(best);
-                unsigned m = __ballot_sync(0xffffffffu, best == wv);
-                int src = m ? (__ffs(m) - 1) : 0;
-                int ws_ = __shfl_sync(0xffffffffu, bslot, src);
-                __syncwarp();
-                if (lane == 0) red_row[par][warp] = make_int4(__float_as_int(wv), ws_, ws_ >= 0 ? (int)near[ws_] : -1, 0);
-            }
-            if (warp == 0 && ((rec_i & 31) == 0 || !draws_valid)) {
-                // step scalars (fill clock + coordinates of a would-be new electron) of the 32 steps of this block
-                // of records, one Philox call per lane: counter-based, so step k gets the same words as if it were
-                // drawn on its own.  Double-buffered: the other buffer may still be read by a warp that is late in
-                // the previous step.
-                uint32_t c0 = 0u, c1 = (uint32_t)((rec_i & ~31) + lane), c2 = rid_lo, c3 = rid_hi | (DOM_SCALAR << 28);
-                philox4x32_10(c0, c1, c2, c3, K);
-                uint32_t *d = stepdraw[(rec_i >> 5) & 1][lane];
-                d[0] = c0; d[1] = c1; d[2] = c2; d[3] = c3;
-            }
-            draws_valid = true;
-#ifdef MCL_PROFILE_SKEW
-            { const long long now = clock64(); pf_sweep += now - pf_t; pf_t = now; }
-#endif
-            cta_sync<NT>();                                   // ===== B1
-#ifdef MCL_PROFILE_SKEW
-            { const long long now = clock64(); pf_wait += now - pf_t; pf_t = now; pf_steps++; pf_m = now; }
-#endif
-            float vmin; int smin, hmin;
-            {
-                const int4 row = lane < NW ? red_row[par][lane] : make_int4(__float_as_int(F_INF), -1, -1, 0);
-                const float v = __int_as_float(row.x);
-                const int s = row.y, hh = row.z;
-                vmin = warp_min_f32(v);
-                unsigned m = __ballot_sync(0xffffffffu, v == vmin);
-                const int src = m ? (__ffs(m) - 1) : 0;
-                smin = __shfl_sync(0xffffffffu, s, src);
-                hmin = __shfl_sync(0xffffffffu, hh, src);
-            }
-            // ---------------- filling clock (tl_trap_lab.py:53-60) and dt (simulate.py:58-60)
-            // Without a dose the clock is exponential(1e20 s) >= -ln(1 - 2^-24) * 1e20 = 5.96e12 s: it can only matter (the
-            // reference's spurious fill) when nothing else happens before 5e12 s -- otherwise it is not evaluated.
-            const float dt_rec0 = n_e > 0 ? ex2_fast(vmin) * LN2F : F_INF;
-            float dt_fill = F_INF;
-            if (dose_on || !((lab ? dt_rec0 : fminf(dt_rec0, dt_cap)) < 5.0e12f)) {       // (the lab loops have no step cap)
-                float lam = (n_e == rp.N_e || !dose_on) ? 1e-20f : dose_over_D0 * (float)(rp.N_e - n_e);
-                dt_fill = lam > 0.0f ? __fdividef(-lg2_fast(u01(stepdraw[(rec_i >> 5) & 1][rec_i & 31][0])) * LN2F, lam) : 1e20f;
-            }
-            const float dt_rec = n_e > 0 ? dt_rec0 : dt_fill;
-            float dt; bool is_fill, is_rec;
-            if (!lab) {
-                dt = fminf(fminf(dt_fill, dt_rec), dt_cap);
-                is_fill = (dt == dt_fill);
-                is_rec = !is_fill && (dt == dt_rec);
-            } else {
-                is_fill = (dt_fill <= dt_rec);
-                is_rec = !is_fill;
-                dt = is_fill ? dt_fill : dt_rec;
-            }
-            es32 += (uint32_t)n_e;
-            if (es32 > 0xC0000000u) { esteps += es32; es32 = 0u; }      // the 64-bit total lives in local memory
-            const int n_before = n_e;
-            const double t_new = t_cur + (double)dt;
-
-            MCL_MARK(0)      // reduce + decision
-            // ---------------- fused occupancy histogram: edges passed while n_e was n_before
-            if (hedge_next <= t_new) {
-                // hbin_next <= n_bins; edge n_bins (the right end of the axis) closes the last bin
-                while (hedge_next <= t_new) {
-                    if (tid == 0 && p.hist_occ && hbin_next < p.hist.n_bins) {
-                        size_t q = (size_t)hrow * p.hist.n_bins + hbin_next;
-                        atomicAdd(&p.hist_occ[q], (unsigned long long)n_before);
-                        if (p.hist_occ_sq) atomicAdd(&p.hist_occ_sq[q], (unsigned long long)n_before * (unsigned long long)n_before);
-                    }
-                    hbin_next++;
-                    hedge_next = hbin_next <= p.hist.n_bins ? edge_after(hbin_next, hedge_next) : CUDART_INF;
-                }
-            }
-            t_cur = t_new;
-
-            MCL_MARK(1)      // histogram
-            int ev = 0;
-            if (is_rec) {
-                // ---------------- Box.remove_pair (engine.py:154-175)
-                ev = 1;
-                const int h = hmin;                                    // nearest hole of the winner (read before B1)
-                if (tid == ((smin / SPC) % NT)) { cr[smin] = F_INF; near[smin] = (NearT)NEAR_DEAD; }   // owner tombstones it
-                n_e--;
-                int h2 = -1;
-                if (ever_filled) {
-                    // stale-cache mode: the reference also refreshes electrons cached on the hole that
-                    // FOLLOWS the removed one in index order (shift-then-mask, engine.py:168-171)
-                    const int last_w = (H.n_slots - 1) >> 5;
-                    int w_ = (h + 1) >> 5;
-                    uint32_t bits = w_ <= last_w ? (hole_bm[w_] & (0xffffffffu << ((h + 1) & 31))) : 0u;
-                    while (!bits && w_ < last_w) bits = hole_bm[++w_];
-                    if (bits) { const int j = 32 * w_ + __ffs(bits) - 1; if (j < H.n_slots) h2 = j; }
-                }
-                if (tid == 0) {
-                    hpos[h].x = DEAD_X;
-                    // Bit h is the only bit of the bitmap that changes in this phase, and every concurrent reader
-                    // (retarget below, other warps) skips hole h before it looks at a word: reading the old or the
-                    // new word gives the same answer.  compute-sanitizer racecheck flags exactly this read / RMW
-                    // overlap; it is benign by construction.  The next barrier publishes the bit.
-                    hole_bm[h >> 5] &= ~(1u << (h & 31));
-                    if (hist_on && p.hist_events) {
-                        // edges up to t_cur have been passed: the event sits in the bin before the cursor
-                        const int b = h_mono ? (hbin_next - 1) : bin_of(t_cur);
-                        if (b >= 0 && b < p.hist.n_bins) atomicAdd(&p.hist_events[(size_t)hrow * p.hist.n_bins + b], 1ull);
-                    }
-                }
-                if (h >= n_h0) n_fill_alive--;
-                // Which of MY other electrons were cached on h (or h2)?  A thread owns the pairs it sweeps
-                // (q = tid, tid + NT, ...), and only the owner ever touches cr[] / near[] of a pair outside
-                // barrier-protected phases -- so re-targeting needs no CTA barrier at all.
-                // no other electron can be cached on h if h was never the target of a second one
-                const bool lone = share_bm && !ever_filled &&
-                                  (!((multi_bm[h >> 5] >> (h & 31)) & 1u) ||                    // nobody else at all, or
-                                   !((ref4[h >> 3] >> (4 * (h & 7) + my_group)) & 1u));         // nobody in MY warp group (warp-uniform)
-                int redo = -1;                      // a slot of mine that needs the warp-cooperative search
-                auto retarget = [&](int sl) {
-                    bool fixed = false;
-                    if (!ever_filled) {
-                        // no hole was ever added: the new nearest is the first remembered candidate that is
-                        // still alive (and is not the hole dying now, whose bitmap bit may not be visible yet)
-                        // distances and slots of the list are fetched together: ONE round trip to L2 / HBM
-                        const float4 d4 = cand_d[sl];
-                        uint32_t cj[KC];
-                        if (sizeof(NearT) == 2) {
-                            const uint2 v = *reinterpret_cast<const uint2 *>(cand_j + (size_t)sl * KC);
-                            cj[0] = v.x & 0xffffu; cj[1] = v.x >> 16; cj[2] = v.y & 0xffffu; cj[3] = v.y >> 16;
-                        } else {
-                            const uint4 v = *reinterpret_cast<const uint4 *>(cand_j + (size_t)sl * KC);
-                            cj[0] = v.x; cj[1] = v.y; cj[2] = v.z; cj[3] = v.w;
-                        }
-                        const float dk[KC] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-                        for (int c = 0; c < KC; c++) {
-                            const uint32_t j = cj[c];
-                            if (!fixed && j != NEAR_DEAD && j != (uint32_t)h && ((hole_bm[j >> 5] >> (j & 31)) & 1u)) {
-                                cr[sl] = dk[c]; near[sl] = (NearT)j; fixed = true;
-                                if (share_bm) mark_target(j, sl);
-                            }
+                            need |= __ballot_sync(0xffffffffu, lane == src && redo >= 0) ;
                         }
                     }
-                    return fixed;
-                };
-                auto scan = [&](auto two_targets) {
-                    constexpr bool TWO = decltype(two_targets)::value;
-                    constexpr int NWORD = SPC * (int)sizeof(NearT) / 4;       // 32-bit words of near[] per chunk
-                    // chunks whose loads are in flight together (narrow CTAs: few chunks per thread, and their 16 CTAs per SM
-                    // at different phases feel every extra kilobyte of code in the instruction cache)
-                    constexpr int SU = NT >= 256 ? MCL_SCAN_UNROLL : MCL_SCAN_UNROLL_NARROW;
-                    const uint32_t hh = (uint32_t)h * 0x00010001u, hh2 = (uint32_t)h2 * 0x00010001u;
-                    for (int b0 = tid; b0 < n_chunks; b0 += SU * NT) {
-                        uint32_t w[SU][NWORD];
+                    MCL_MARK(4)  // warp searches
+                    // ---------------- compaction: keep tombstones below 1/TOMB_DIV of the slots in use.  The Philox counter of a
+                    // clock is its slot, so WHEN slots move is part of the stream definition: TOMB_DIV is one constant for
+                    // every CTA width (results must not depend on the launch shape).
+                    if ((n_slots - n_e) * TOMB_DIV > n_slots && n_slots >= 64) {
+                        cta_sync<NT>();
+                        int run = 0;
+                        for (int base = 0; base < n_slots; base += NT) {
+                            int s = base + tid;
+                            float c = s < n_slots ? cr[s] : F_INF;
+                            NearT nn = s < n_slots ? near[s] : (NearT)NEAR_DEAD;
+                            bool alive = c < F_INF;
+                            float x = 0.f, y = 0.f, z = 0.f;
+                            float4 cd = make_float4(0.f, 0.f, 0.f, 0.f);
+                            NearT cj[KC];
 #pragma unroll
-                        for (int u = 0; u < SU; u++) {
-                            const int b = b0 + u * NT;
-                            if (u > 0 && b >= n_chunks) {             // past the end: the empty-slot pattern matches no hole
+                            for (int k = 0; k < KC; k++) cj[k] = (NearT)NEAR_DEAD;
+                            if (alive) {
+                                x = ex[s]; y = ey[s]; z = ez[s];
+                                if (!ever_filled) {
+                                    cd = cand_d[s];
 #pragma unroll
-                                for (int k = 0; k < NWORD; k++) w[u][k] = 0xffffffffu;
-                            } else if (NWORD == 4) {
-                                const uint4 v = reinterpret_cast<const uint4 *>(near)[b];
-                                w[u][0] = v.x; w[u][1 % NWORD] = v.y; w[u][2 % NWORD] = v.z; w[u][3 % NWORD] = v.w;
-                            } else {
-                                const uint2 v = reinterpret_cast<const uint2 *>(near)[b];
-                                w[u][0] = v.x; w[u][1 % NWORD] = v.y;
-                            }
-                        }
-                        uint32_t hits = 0u;                           // bit u: chunk b0 + u * NT may hold a match
-#pragma unroll
-                        for (int u = 0; u < SU; u++) {
-                            bool hit;
-                            if (sizeof(NearT) == 2) {
-                                // 16-bit slots: zero-halfword test (false positives possible, re-checked below)
-                                auto zh = [](uint32_t t) { return (t - 0x00010001u) & ~t & 0x80008000u; };
-                                uint32_t z = 0u;
-#pragma unroll
-                                for (int k = 0; k < NWORD; k++) { z |= zh(w[u][k] ^ hh); if (TWO) z |= zh(w[u][k] ^ hh2); }
-                                hit = z != 0u;
-                            } else {
-                                hit = false;
-#pragma unroll
-                                for (int k = 0; k < NWORD; k++) { hit |= (w[u][k] == (uint32_t)h); if (TWO) hit |= (w[u][k] == (uint32_t)h2); }
-                            }
-                            hits |= hit ? (1u << u) : 0u;
-                        }
-                        while (hits) {
-                            const int b = b0 + (__ffs(hits) - 1) * NT;
-                            hits &= hits - 1u;
-                            for (int k = 0; k < SPC; k++) {
-                                const int sl = SPC * b + k;
-                                const uint32_t nn = near[sl];
-                                if ((nn == (uint32_t)h || (TWO && nn == (uint32_t)h2)) && sl != smin && lone) atomicOr(&s_err, 1);
-                                if ((nn == (uint32_t)h || (TWO && nn == (uint32_t)h2)) && sl != smin && !retarget(sl)) {
-                                    // rare: park it until the warp search below
-                                    if (redo >= 0) cr[sl] = -1.0f;      // more than one: mark, found again below
-                                    else redo = sl;
+                                    for (int k = 0; k < KC; k++) cj[k] = cand_j[(size_t)s * KC + k];
                                 }
                             }
+                            unsigned m = __ballot_sync(0xffffffffu, alive);
+                            int wpre = __popc(m & ((1u << lane) - 1u));
+                            if (lane == 0) s_scan[warp] = __popc(m);
+                            cta_sync<NT>();
+                            int woff = 0, tot = 0;
+#pragma unroll
+                            for (int k = 0; k < NW; k++) { int v = s_scan[k]; if (k < warp) woff += v; tot += v; }
+                            int dst = run + woff + wpre;
+                            cta_sync<NT>();                       // all reads of this tile done
+                            if (alive) {
+                                cr[dst] = c; near[dst] = nn; ex[dst] = x; ey[dst] = y; ez[dst] = z;
+                                if (!ever_filled) {
+                                    cand_d[dst] = cd;
+#pragma unroll
+                                    for (int k = 0; k < KC; k++) cand_j[(size_t)dst * KC + k] = cj[k];
+                                }
+                            }
+                            run += tot;
+                        }
+                        cta_sync<NT>();
+                        for (int s = run + tid; s < n_slots; s += NT) { cr[s] = F_INF; near[s] = (NearT)NEAR_DEAD; }
+                        n_slots = run;
+                        cta_sync<NT>();
+                        if (share_bm && !ever_filled) {           // slots changed owners: rebuild the warp-group reference mask
+                            for (int w = tid; w < cfg.ref_words; w += NT) ref4[w] = 0u;
+                            cta_sync<NT>();
+                            for (int sl = tid; sl < n_slots; sl += NT) {
+                                const uint32_t j = near[sl];
+                                if (j != NEAR_DEAD) atomicOr(&ref4[j >> 3], 1u << (4 * (j & 7) + group_of_slot(sl)));
+                            }
+                            cta_sync<NT>();
                         }
                     }
-                };
-                MCL_MARK(2)  // retire the pair
-                if (!lone || verify_skip) { if (h2 >= 0) scan(std::true_type{}); else scan(std::false_type{}); }
-                MCL_MARK(3)  // scan + re-target from the lists
-                // Exhausted lists and fill mode (new holes become visible on a re-search, engine.py:171-175):
-                // the owner's WARP searches the cell grid cooperatively; still no CTA barrier.
-                {
-                    unsigned need = __ballot_sync(0xffffffffu, redo >= 0);
-                    while (need) {
-                        const int src = __ffs(need) - 1;
-                        need &= need - 1;
-                        const int sl = __shfl_sync(0xffffffffu, redo, src);
-                        unsigned long long b = warp_nearest(H, ex[sl], ey[sl], ez[sl], lane, h);
-                        if (lane == src) {
-                            cr[sl] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[sl] = (NearT)(uint32_t)b;
-                            if (share_bm && !ever_filled) mark_target((uint32_t)b, sl);
-                            // further parked slots of this lane were marked with cr = -1
-                            redo = -1;
-                            for (int b = tid; b < n_chunks && redo < 0; b += NT)
-                                for (int k = 0; k < SPC && redo < 0; k++)
-                                    if (cr[SPC * b + k] == -1.0f) redo = SPC * b + k;
-                        }
-                        need |= __ballot_sync(0xffffffffu, lane == src && redo >= 0) ;
-                    }
-                }
-                MCL_MARK(4)  // warp searches
-                // ---------------- compaction: keep tombstones below 1/TOMB_DIV of the slots in use.  The Philox counter of a
-                // clock is its slot, so WHEN slots move is part of the stream definition: TOMB_DIV is one constant for
-                // every CTA width (results must not depend on the launch shape).
-                if ((n_slots - n_e) * TOMB_DIV > n_slots && n_slots >= 64) {
-                    cta_sync<NT>();
-                    int run = 0;
-                    for (int base = 0; base < n_slots; base += NT) {
-                        int s = base + tid;
-                        float c = s < n_slots ? cr[s] : F_INF;
-                        NearT nn = s < n_slots ? near[s] : (NearT)NEAR_DEAD;
-                        bool alive = c < F_INF;
-                        float x = 0.f, y = 0.f, z = 0.f;
-                        float4 cd = make_float4(0.f, 0.f, 0.f, 0.f);
-                        NearT cj[KC];
-#pragma unroll
-                        for (int k = 0; k < KC; k++) cj[k] = (NearT)NEAR_DEAD;
-                        if (alive) {
-                            x = ex[s]; y = ey[s]; z = ez[s];
-                            if (!ever_filled) {
-                                cd = cand_d[s];
-#pragma unroll
-                                for (int k = 0; k < KC; k++) cj[k] = cand_j[(size_t)s * KC + k];
+                } else if (is_fill) {
+                    // ---------------- Box.add_electron (engine.py:133-152), done by warp 0
+                    ever_filled = true;
+                    int es = -1;
+                    if (n_e == n_slots) es = n_slots;             // no tombstone to reuse
+                    const bool append_e = (es >= 0);
+                    if (append_e && es >= cfg.cap_slots - 4) { status = MCL_ERR_CAPACITY; break; }
+                    const bool append_h = (n_fill_alive == H.n_slots - n_h0);
+                    if (append_h && H.n_slots >= p.cap_h) { status = MCL_ERR_CAPACITY; break; }
+                    if (warp == 0) {
+                        if (!append_e) {
+                            for (int base = 0; base < n_slots && es < 0; base += 32) {
+                                int s = base + lane;
+                                unsigned m = __ballot_sync(0xffffffffu, s < n_slots && !(cr[s] < F_INF));
+                                if (m) es = base + __ffs(m) - 1;
                             }
                         }
-                        unsigned m = __ballot_sync(0xffffffffu, alive);
-                        int wpre = __popc(m & ((1u << lane) - 1u));
-                        if (lane == 0) s_scan[warp] = __popc(m);
-                        cta_sync<NT>();
-                        int woff = 0, tot = 0;
-#pragma unroll
-                        for (int k = 0; k < NW; k++) { int v = s_scan[k]; if (k < warp) woff += v; tot += v; }
-                        int dst = run + woff + wpre;
-                        cta_sync<NT>();                       // all reads of this tile done
-                        if (alive) {
-                            cr[dst] = c; near[dst] = nn; ex[dst] = x; ey[dst] = y; ez[dst] = z;
-                            if (!ever_filled) {
-                                cand_d[dst] = cd;
-#pragma unroll
-                                for (int k = 0; k < KC; k++) cand_j[(size_t)dst * KC + k] = cj[k];
+                        int hs = H.n_slots;
+                        if (!append_h) {
+                            hs = -1;
+                            for (int base = n_h0; base < H.n_slots && hs < 0; base += 32) {
+                                int j = base + lane;
+                                unsigned m = __ballot_sync(0xffffffffu, j < H.n_slots && !((hole_bm[j >> 5] >> (j & 31)) & 1u));
+                                if (m) hs = base + __ffs(m) - 1;
                             }
                         }
-                        run += tot;
+                        const uint32_t *sd = stepdraw[(rec_i >> 5) & 1][rec_i & 31];
+                        float nx = u01(sd[1]) * core_s, ny = u01(sd[2]) * core_s, nz = u01(sd[3]) * core_s;
+                        uint32_t d0 = 1u, d1 = (uint32_t)rec_i, d2 = rid_lo, d3 = rid_hi | (DOM_SCALAR << 28);
+                        philox4x32_10(d0, d1, d2, d3, K);
+                        float qx = u01(d0) * bnd_s, qy = u01(d1) * bnd_s, qz = u01(d2) * bnd_s;
+                        unsigned long long b = warp_nearest(H, nx, ny, nz, lane);     // OLD holes only
+                        if (lane == 0) {
+                            ex[es] = nx; ey[es] = ny; ez[es] = nz;
+                            cr[es] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[es] = (NearT)(uint32_t)b;
+                            hpos[hs] = make_float4(qx, qy, qz, __int_as_float(hs));
+                            hole_bm[hs >> 5] |= 1u << (hs & 31);
+                        }
                     }
+                    if (append_e) n_slots++;
+                    if (append_h) H.n_slots++;
+                    n_fill_alive++;
+                    n_e++;
                     cta_sync<NT>();
-                    for (int s = run + tid; s < n_slots; s += NT) { cr[s] = F_INF; near[s] = (NearT)NEAR_DEAD; }
-                    n_slots = run;
-                    cta_sync<NT>();
-                    if (share_bm && !ever_filled) {           // slots changed owners: rebuild the warp-group reference mask
-                        for (int w = tid; w < cfg.ref_words; w += NT) ref4[w] = 0u;
-                        cta_sync<NT>();
-                        for (int sl = tid; sl < n_slots; sl += NT) {
-                            const uint32_t j = near[sl];
-                            if (j != NEAR_DEAD) atomicOr(&ref4[j >> 3], 1u << (4 * (j & 7) + group_of_slot(sl)));
-                        }
-                        cta_sync<NT>();
-                    }
                 }
-            } else if (is_fill) {
-                // ---------------- Box.add_electron (engine.py:133-152), done by warp 0
-                ever_filled = true;
-                int es = -1;
-                if (n_e == n_slots) es = n_slots;             // no tombstone to reuse
-                const bool append_e = (es >= 0);
-                if (append_e && es >= cfg.cap_slots - 4) { status = MCL_ERR_CAPACITY; break; }
-                const bool append_h = (n_fill_alive == H.n_slots - n_h0);
-                if (append_h && H.n_slots >= p.cap_h) { status = MCL_ERR_CAPACITY; break; }
-                if (warp == 0) {
-                    if (!append_e) {
-                        for (int base = 0; base < n_slots && es < 0; base += 32) {
-                            int s = base + lane;
-                            unsigned m = __ballot_sync(0xffffffffu, s < n_slots && !(cr[s] < F_INF));
-                            if (m) es = base + __ffs(m) - 1;
-                        }
-                    }
-                    int hs = H.n_slots;
-                    if (!append_h) {
-                        hs = -1;
-                        for (int base = n_h0; base < H.n_slots && hs < 0; base += 32) {
-                            int j = base + lane;
-                            unsigned m = __ballot_sync(0xffffffffu, j < H.n_slots && !((hole_bm[j >> 5] >> (j & 31)) & 1u));
-                            if (m) hs = base + __ffs(m) - 1;
-                        }
-                    }
-                    const uint32_t *sd = stepdraw[(rec_i >> 5) & 1][rec_i & 31];
-                    float nx = u01(sd[1]) * core_s, ny = u01(sd[2]) * core_s, nz = u01(sd[3]) * core_s;
-                    uint32_t d0 = 1u, d1 = (uint32_t)rec_i, d2 = rid_lo, d3 = rid_hi | (DOM_SCALAR << 28);
-                    philox4x32_10(d0, d1, d2, d3, K);
-                    float qx = u01(d0) * bnd_s, qy = u01(d1) * bnd_s, qz = u01(d2) * bnd_s;
-                    unsigned long long b = warp_nearest(H, nx, ny, nz, lane);     // OLD holes only
-                    if (lane == 0) {
-                        ex[es] = nx; ey[es] = ny; ez[es] = nz;
-                        cr[es] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[es] = (NearT)(uint32_t)b;
-                        hpos[hs] = make_float4(qx, qy, qz, __int_as_float(hs));
-                        hole_bm[hs >> 5] |= 1u << (hs & 31);
-                    }
-                }
-                if (append_e) n_slots++;
-                if (append_h) H.n_slots++;
-                n_fill_alive++;
-                n_e++;
-                cta_sync<NT>();
-            }
 
-            MCL_MARK(5)      // compaction / fill
-            // ---------------- record (simulate.py:64,85-89): staged, flushed 32 at a time
-            if (trace && tid == 0) { rec_ev[rec_i & 31] = ev; rec_ne[rec_i & 31] = n_e; rec_t[rec_i & 31] = t_off + t_cur; }
-            rec_i++;
-            if ((rec_i & 31) == 0) flush_records(32);
-            if (iso) {
-                while (obs_idx < rp.obs_count && t_cur >= obs[obs_idx]) {
-                    if (tid == 0 && p.obs_n_e) p.obs_n_e[rp.obs_begin + obs_idx] = n_e;
-                    obs_idx++;
+                MCL_MARK(5)      // compaction / fill
+                // ---------------- record (simulate.py:64,85-89): staged, flushed 32 at a time
+                if (trace && tid == 0) { rec_ev[rec_i & 31] = ev; rec_ne[rec_i & 31] = n_e; rec_t[rec_i & 31] = t_off + t_cur; }
+                rec_i++;
+                if (trace && (rec_i & 31) == 0) flush_records(32);
+                if (iso) {
+                    while (obs_idx < rp.obs_count && t_cur >= obs[obs_idx]) {
+                        if (tid == 0 && p.obs_n_e) p.obs_n_e[rp.obs_begin + obs_idx] = n_e;
+                        obs_idx++;
+                    }
                 }
+                if (!lab && S.duration != 0.0 && t_cur >= S.duration) break;          // simulate.py:91-92
             }
-            if (!lab && S.duration != 0.0 && t_cur >= S.duration) break;          // simulate.py:91-92
-        }
+            }
+            return true;
+        };
+        if (!(MCL_FAST_LOOP && cfg.fast && !lab && !trace && !verify_skip && !dose_on && !ever_filled && step_loop(std::true_type{})))
+            step_loop(std::false_type{});
         t_off += t_cur;
         if (lab) break;
     }
@@ -1213,7 +1238,9 @@ static cudaError_t launch_one(const LaunchParams &p, const RoundKeys &K, const C
 cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_slots*/)
 {
     PhiloxPlan pl = make_plan(p.cap_e, p.cap_h, g_nt_override, p.n_replicas);
-    Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.share_bm, pl.ref_words, pl.off_holes, pl.off_cand};
+    int fast = 1;
+    if (const char *env = getenv("MCL_PHILOX_FAST")) fast = atoi(env) != 0;        // knob: 0 = general step loop only
+    Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.share_bm, pl.ref_words, pl.off_holes, pl.off_cand, fast};
     RoundKeys K;
     uint64_t s = mix64(p.seed);
     uint32_t k0 = (uint32_t)s, k1 = (uint32_t)(s >> 32);

@@ -273,3 +273,42 @@ def test_scan_skip_bitmaps_never_hide_a_cached_electron(gpu, which):
     for mode in ("1", "2"):
         assert np.array_equal(runs[mode].event, runs["0"].event) and np.array_equal(runs[mode].n_e, runs["0"].n_e)
         assert np.array_equal(runs[mode].t, runs["0"].t)
+
+
+def test_specialised_step_loop_changes_no_result(gpu):
+    """Legs of the simulate protocol without a dose and without per-step records run a specialised copy of the step
+    loop (protocol / dose / trace / fill-mode branches compiled out; the general loop takes over when the filling
+    clock could matter).  Histograms, final occupancies, step and electron-step counts must equal those of the
+    general loop -- selected with `MCL_PHILOX_FAST=0`, and, independently, by asking for the per-step trace."""
+    import os
+    from mcluminescence_b200 import engine, workloads
+    from tests.test_gpu_philox import CASES, ensemble_tables
+    jobs = [workloads.c2(n_replicas=12), workloads.c5(n_replicas=300), two_leg_workload(R=40, n_e=600),
+            workloads.c2(n_replicas=6, n_e=5000, physics_overrides=["physics_fp.E_loc_2=1.0", "physics_fp.Retrap=0.3"])]
+    # a box that runs empty (n_e reaches 0: the reference's filling clock then decides, general loop) and a ramp
+    for name in ("tl_ramp", "cb_channel"):
+        reps, segs, steps = ensemble_tables(CASES[name][0], 64)
+        jobs.append(dict(name=name, replicas=reps, segments=segs, max_steps=steps, hist=None))
+    empty = two_leg_workload(R=16, n_e=40)
+    empty["segments"]["duration"] = [1e6, 1e9]
+    empty["max_steps"] = 4000
+    jobs.append(empty)
+    for wl in jobs:
+        def go(trace):
+            return engine.run_replicas(wl["replicas"], wl["segments"], wl["max_steps"], seed=43, hist=wl.get("hist"),
+                                       trace=trace, sync=True)
+        fast = go(False)
+        with_trace = go(True)
+        os.environ["MCL_PHILOX_FAST"] = "0"
+        try:
+            general = go(False)
+        finally:
+            del os.environ["MCL_PHILOX_FAST"]
+        for other in (with_trace, general):
+            assert np.array_equal(fast.status, other.status), wl["name"]
+            assert np.array_equal(fast.steps_used, other.steps_used), wl["name"]
+            assert np.array_equal(fast.final_n_e, other.final_n_e) and np.array_equal(fast.esteps, other.esteps), wl["name"]
+            if wl.get("hist") is not None:
+                assert np.array_equal(fast.hist_events, other.hist_events), wl["name"]
+                assert np.array_equal(fast.hist_occ, other.hist_occ), wl["name"]
+    assert int(jobs[-1]["replicas"]["n_e0"][0]) > 0 and int(fast.final_n_e.min()) == 0     # the last job did run empty
