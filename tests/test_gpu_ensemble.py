@@ -285,7 +285,8 @@ def test_specialised_step_loop_changes_no_result(gpu):
     from tests.test_gpu_philox import CASES, ensemble_tables
     jobs = [workloads.c2(n_replicas=12), workloads.c5(n_replicas=300), two_leg_workload(R=40, n_e=600),
             workloads.c2(n_replicas=6, n_e=5000, physics_overrides=["physics_fp.E_loc_2=1.0", "physics_fp.Retrap=0.3"])]
-    # a box that runs empty (n_e reaches 0: the reference's filling clock then decides, general loop) and a ramp
+    # ramps (conduction-band channel on and off) and, last, boxes that run almost empty: their final steps have no clock
+    # below 5e12 s, which is where the specialised loop hands the step over to the general one
     for name in ("tl_ramp", "cb_channel"):
         reps, segs, steps = ensemble_tables(CASES[name][0], 64)
         jobs.append(dict(name=name, replicas=reps, segments=segs, max_steps=steps, hist=None))
@@ -311,4 +312,5 @@ def test_specialised_step_loop_changes_no_result(gpu):
             if wl.get("hist") is not None:
                 assert np.array_equal(fast.hist_events, other.hist_events), wl["name"]
                 assert np.array_equal(fast.hist_occ, other.hist_occ), wl["name"]
-    assert int(jobs[-1]["replicas"]["n_e0"][0]) > 0 and int(fast.final_n_e.min()) == 0     # the last job did run empty
+    # the last job ends with a handful of electrons whose next clock is beyond 5e12 s: the hand-over step
+    assert 0 < int(fast.final_n_e.max()) < int(jobs[-1]["replicas"]["n_e0"][0]) // 2
