@@ -189,3 +189,40 @@ def test_tltrapsim_api_in_philox_mode(gpu, capsys):
     with pytest.raises(TypeError):
         bad = initialize_runs(compose(overrides=["exp_type_fp=TLlab", "physics_fp=BG_basic"]))[0]
         TLTrapSim(bad)
+
+
+@pytest.mark.parametrize("T_c,A_opt", [(50.0, 100.0), (250.0, 0.0)])
+def test_decay_follows_the_nearest_neighbour_integral(gpu, T_c, A_opt):
+    """Analytic pin (no oracle involved): with many more holes than electrons the kernel's decay must follow the
+    nearest-neighbour integral of the localized-transition model for `k0 = A_opt + b e^{-E_loc/kT}` -- optical and
+    thermal prefactor alike (same check as tests/test_oracle_analytic.py, same tolerance)."""
+    from mcluminescence_b200 import engine
+    from tests import test_oracle_analytic as ana
+    cfg_overrides = [f"exp_type_fp.N_e={ana.N_E}", f"exp_type_fp.holes={ana.HOLES}", "exp_type_fp.e_ratio_start=1.0",
+                     f"exp_type_fp.T_start=[{T_c}]", "exp_type_fp.T_rate=[0]", "exp_type_fp.duration=[1]",
+                     "exp_type_fp.steps=400", "exp_type_fp.sims=1"]
+    reps, segs, steps = ensemble_tables(cfg_overrides, ana.R)
+    b, E, kb, rho_p = 1e12, 1.2, 8.617343e-05, 3e-4            # shipped basicTL12 / TL12 values (asserted below)
+    from mcluminescence_b200.config import compose
+    cfg = compose(overrides=cfg_overrides)
+    assert (float(cfg["physics_fp"]["b"]), float(cfg["physics_fp"]["E_loc_1"]), float(cfg["physics_fp"]["k_b"]),
+            float(cfg["exp_type_fp"]["rho_prime"])) == (b, E, kb, rho_p)
+    k0 = A_opt + b * np.exp(-E / (kb * (T_c + 273.15)))
+    grid = np.array([1e3, 1e4, 1e5, 1e6, 3e6, 1e7]) / k0
+    segs["A_opt"] = A_opt
+    segs["duration"] = float(grid[-1])
+    out = engine.run_replicas(reps, segs, steps, seed=int(5 + T_c), sync=True)
+    out.raise_on_error()
+    frac = np.zeros((ana.R, len(grid)))
+    for r in range(ana.R):
+        n = int(out.steps_used[r])
+        t, ne = out.t[r, :n], out.n_e[r, :n]
+        idx = np.searchsorted(t, grid, side="right") - 1
+        frac[r] = np.where(idx >= 0, ne[np.maximum(idx, 0)], ana.N_E) / ana.N_E
+    got, se = frac.mean(axis=0), frac.std(axis=0, ddof=1) / np.sqrt(ana.R)
+    want = ana.survival(k0, grid, rho_p)
+    assert np.all(np.abs(got - want) <= 4.0 * se + 0.004), (got, want, se)
+    # the specialised step loop (no trace): final occupancy only
+    fin = engine.run_replicas(reps, segs, steps, seed=int(5 + T_c), trace=False, sync=True)
+    fin.raise_on_error()
+    assert np.array_equal(fin.final_n_e, out.final_n_e)
