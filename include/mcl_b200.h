@@ -74,15 +74,18 @@ typedef struct mcl_replica {
 } mcl_replica;
 
 /* Fused ensemble reduction (replaces the per-replica loops of plots.py:50-74 for ensembles):
- * every replica adds its events / occupancy to row `group[r]` of integer histograms on a common
- * axis.  Integer accumulation => results do not depend on block order or on the GPU count. */
+ * leg `sg` of replica r adds its events / occupancy to row `hist_group[r] + sg` of integer
+ * histograms on a common axis (`hist_group[r]` = row of the replica's FIRST leg; without
+ * hist_group every replica starts at row 0).  The buffers have `n_groups` rows; mcl_run rejects
+ * (MCL_ERR_ARG) any replica whose rows [hist_group[r], hist_group[r] + seg_count) do not fit.
+ * Integer accumulation => results do not depend on block order or on the GPU count. */
 #define MCL_AXIS_TIME_LIN  0   /* bin k covers [lo + k*w, lo + (k+1)*w)                  */
 #define MCL_AXIS_TIME_LOG  1   /* log10(t) linear between log10(lo) and log10(hi)        */
 #define MCL_AXIS_TEMP      2   /* T_start + T_rate * t of the active segment, deg C      */
 typedef struct mcl_hist_spec {
     int32_t axis;
     int32_t n_bins;
-    int32_t n_groups;
+    int32_t n_groups;            /* ROWS of the three histogram buffers */
     int32_t reserved;
     double  lo, hi;
 } mcl_hist_spec;
@@ -115,7 +118,7 @@ typedef struct mcl_run_args {
     int32_t *obs_n_e;              /* [n_obs] ISO_lab: n_e at each observation crossing             */
     /* ---- fused ensemble histograms, DEVICE memory, optional ---- */
     const mcl_hist_spec *hist;     /* HOST; NULL = no histogram                                     */
-    const int32_t *hist_group;     /* HOST [R] row of each replica; NULL = all in row 0             */
+    const int32_t *hist_group;     /* HOST [R] row of each replica's first leg; NULL = row 0        */
     int64_t *hist_events;          /* DEVICE [n_groups, n_bins] recombinations per bin (ADDED to)   */
     int64_t *hist_occ;             /* DEVICE [n_groups, n_bins] sum of n_e at each bin's left edge  */
     int64_t *hist_occ_sq;          /* DEVICE [n_groups, n_bins] sum of n_e^2 (for the spread)       */
@@ -159,7 +162,10 @@ typedef struct mcl_lab {
 } mcl_lab;
 int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uint64_t seed,
                   uint64_t candidate_id0, double *mse, int64_t *esteps_total, void *stream);
-/* mcl_objective keeps its (multi-GB) device scratch between calls; this frees it. */
+/* mcl_objective keeps its (multi-GB) device scratch between calls (per device, grow-only) and is
+ * therefore serialised internally: concurrent calls from several host threads are safe but run one
+ * after another.  mcl_release_scratch frees the slabs of every device (waiting for a running call)
+ * and leaves the caller's current device unchanged. */
 void mcl_release_scratch(void);
 
 /* Issue-rate microbenchmarks for the roofline denominators (SFU, FP32 FMA, INT32 multiply-add,
@@ -169,6 +175,12 @@ typedef struct mcl_peaks {
     int32_t n_sm, reserved;
 } mcl_peaks;
 int mcl_device_peaks(mcl_peaks *out);
+
+/* Test hook: the native kernel's exponential draw for raw Philox words, evaluated on the device:
+ * neg_lg2_u[i] = -lg2.approx(u01(words[i])) (the waiting time in units of ln 2 / rate) and
+ * lg2_of_that[i] = lg2.approx(neg_lg2_u[i]) (what enters the log-domain argmin).  All pointers HOST.
+ * tests/test_gpu_philox.py pins the small-waiting-time tail with it. */
+int mcl_debug_exp_draws(const uint32_t *words, int32_t n, float *neg_lg2_u, float *lg2_of_that);
 
 const char *mcl_last_error(void);
 int mcl_abi_version(void);

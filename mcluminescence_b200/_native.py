@@ -14,7 +14,7 @@ ABI_VERSION = 1
 
 EXPORTS = (
     "mcl_abi_version", "mcl_last_error", "mcl_workspace_bytes", "mcl_run", "mcl_run_host",
-    "mcl_device_peaks", "mcl_objective", "mcl_release_scratch",
+    "mcl_device_peaks", "mcl_objective", "mcl_release_scratch", "mcl_debug_exp_draws",
 )
 
 
@@ -74,14 +74,24 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("MCL_B200_LIB", _build.LIB_PATH)      # override: A/B builds while tuning
-    if not os.path.isfile(path):
+    override = os.environ.get("MCL_B200_LIB")                   # override: A/B builds while tuning
+    if override:
+        if not os.path.isfile(override):
+            raise NativeError(f"MCL_B200_LIB names a missing file: {override}")
+        path = override
+    else:
+        path = _build.LIB_PATH
+        # build() recompiles whatever is older than its sources (mtime), so an edited kernel is never
+        # silently tested against a stale library; without nvcc an existing library is used as is
         try:
             _build.build()
         except Exception as exc:  # noqa: BLE001
-            raise NativeError(
-                f"libmcl_b200.so is missing and could not be built ({exc}); "
-                "the kinetics path has no CPU fallback") from exc
+            if not os.path.isfile(path):
+                raise NativeError(
+                    f"libmcl_b200.so is missing and could not be built ({exc}); "
+                    "the kinetics path has no CPU fallback") from exc
+            if _build.have_nvcc():
+                raise NativeError(f"libmcl_b200.so is stale and the rebuild failed: {exc}") from exc
     L = C.CDLL(path)
     L.mcl_abi_version.restype = C.c_int
     L.mcl_last_error.restype = C.c_char_p
@@ -97,6 +107,8 @@ def load():
         L.mcl_objective.restype = C.c_int
         L.mcl_objective.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Lab), C.c_uint64, C.c_uint64,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcl_debug_exp_draws.restype = C.c_int
+    L.mcl_debug_exp_draws.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     if L.mcl_abi_version() != ABI_VERSION:
         raise NativeError(f"libmcl_b200.so ABI {L.mcl_abi_version()} != expected {ABI_VERSION}")
     _lib = L

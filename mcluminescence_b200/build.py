@@ -33,30 +33,64 @@ def nvcc() -> str:
     return exe
 
 
-def _stale(target: str, deps) -> bool:
-    if not os.path.isfile(target):
+def have_nvcc() -> bool:
+    try:
+        nvcc()
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps)
+    except RuntimeError:
+        return False
+
+
+def _digest(paths, extra=()) -> str:
+    """Content fingerprint of a compilation unit: sources, headers and flags.  (mtimes do not survive the
+    copy to the GPU box, and a stale library must never be loaded silently.)"""
+    import hashlib
+    h = hashlib.sha256()
+    for p in paths:
+        with open(p, "rb") as fh:
+            h.update(fh.read())
+        h.update(b"\0")
+    h.update("\0".join(extra).encode())
+    return h.hexdigest()
+
+
+def _stamp_ok(target: str, digest: str) -> bool:
+    try:
+        with open(target + ".stamp") as fh:
+            return os.path.isfile(target) and fh.read().strip() == digest
+    except OSError:
+        return False
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile what is out of date (by content fingerprint) and link.  Safe to call from several processes
+    at once (one rank per GPU): a file lock serialises them and the later ones find everything fresh."""
+    import fcntl
     os.makedirs(LIB_DIR, exist_ok=True)
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     headers.append(os.path.join(INCLUDE, "mcl_b200.h"))
-    objs = []
-    for src in SOURCES:
-        sp = os.path.join(CSRC, src)
-        if not os.path.isfile(sp):
-            continue
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        objs.append(obj)
-        if force or _stale(obj, [sp] + headers):
-            cmd = [nvcc()] + ARCH + COMMON + EXTRA.get(src, []) + (["-Xptxas", "-v"] if verbose else []) \
-                + ["-c", sp, "-o", obj]
-            subprocess.run(cmd, check=True)
-    if force or _stale(LIB_PATH, objs):
-        subprocess.run([nvcc()] + ARCH + ["-shared", "-o", LIB_PATH] + objs, check=True)
+    with open(os.path.join(LIB_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        objs, stamps = [], []
+        for src in SOURCES:
+            sp = os.path.join(CSRC, src)
+            if not os.path.isfile(sp):
+                continue
+            obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
+            flags = ARCH + COMMON + EXTRA.get(src, [])
+            dg = _digest([sp] + headers, flags)
+            objs.append(obj)
+            stamps.append(dg)
+            if force or not _stamp_ok(obj, dg):
+                cmd = [nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", obj]
+                subprocess.run(cmd, check=True)
+                with open(obj + ".stamp", "w") as fh:
+                    fh.write(dg)
+        lib_dg = _digest([], stamps)
+        if force or not _stamp_ok(LIB_PATH, lib_dg):
+            subprocess.run([nvcc()] + ARCH + ["-shared", "-o", LIB_PATH] + objs, check=True)
+            with open(LIB_PATH + ".stamp", "w") as fh:
+                fh.write(lib_dg)
     return LIB_PATH
 
 

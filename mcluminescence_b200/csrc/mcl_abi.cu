@@ -31,6 +31,7 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
     }
     if (a->max_steps <= 0) { set_error("mcl_run: max_steps must be positive"); return MCL_ERR_ARG; }
     if (a->mode != MCL_MODE_PHILOX && a->mode != MCL_MODE_REPLAY) { set_error("mcl_run: unknown mode %d", a->mode); return MCL_ERR_ARG; }
+    if (a->hist && (a->hist->n_bins <= 0 || a->hist->n_groups <= 0 || !(a->hist->hi > a->hist->lo))) { set_error("mcl_run: bad histogram spec"); return MCL_ERR_ARG; }
     int ne_max = 0, nh_max = 0, seg_max = 1;
     bool any_dose = false;
     for (int r = 0; r < a->n_replicas; r++) {
@@ -48,6 +49,14 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
         nh_max = std::max(nh_max, rp.n_h0);
         seg_max = std::max(seg_max, rp.seg_count);
         for (int s = 0; s < rp.seg_count; s++) if (a->segments[rp.seg_begin + s].dose_rate != 0.0) any_dose = true;
+        if (a->hist) {
+            // leg sg of replica r writes histogram row hist_group[r] + sg: every such row must exist
+            const int row0 = a->hist_group ? a->hist_group[r] : 0;
+            if (row0 < 0 || row0 + rp.seg_count > a->hist->n_groups) {
+                set_error("replica %d: histogram rows [%d,%d) outside the %d rows of the buffers", r, row0, row0 + rp.seg_count, a->hist->n_groups);
+                return MCL_ERR_ARG;
+            }
+        }
     }
     L->cap_e = ne_max + 8 + seg_max;
     if (a->mode == MCL_MODE_REPLAY) L->cap_h = nh_max + L->cap_e + 8;
@@ -81,7 +90,6 @@ static int run_device(const mcl_run_args *a)
     if (a->mode == MCL_MODE_PHILOX && L.cap_e + 2 > philox_max_slots()) {
         set_error("mcl_run: %d electrons per replica exceed the kernel capacity %d", L.cap_e, philox_max_slots()); return MCL_ERR_CAPACITY;
     }
-    if (a->hist && (a->hist->n_bins <= 0 || a->hist->n_groups <= 0 || !(a->hist->hi > a->hist->lo))) { set_error("mcl_run: bad histogram spec"); return MCL_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)a->stream;
     unsigned char *ws = (unsigned char *)a->workspace;
     CUDA_TRY(cudaMemcpyAsync(ws + L.off_rep, a->replicas, sizeof(mcl_replica) * (size_t)a->n_replicas, cudaMemcpyHostToDevice, st));

@@ -43,6 +43,7 @@ struct DevBuf {
 // by mcl_release_scratch().  This is the only state the library keeps.
 struct ScratchCache {
     std::mutex mu;
+    std::mutex call_mu;          // held for a whole mcl_objective call: calls share the slab, so they are serialised
     void *ptr[64] = {nullptr};
     size_t bytes[64] = {0};
     void *get(size_t need)
@@ -65,8 +66,12 @@ struct ScratchCache {
     }
     void release()
     {
+        std::lock_guard<std::mutex> call_lk(call_mu);        // never under a running call
         std::lock_guard<std::mutex> lk(mu);
+        int cur = -1;
+        const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
         for (int d = 0; d < 64; d++) if (ptr[d]) { cudaSetDevice(d); cudaFree(ptr[d]); ptr[d] = nullptr; bytes[d] = 0; }
+        if (have_cur) cudaSetDevice(cur);                       // leave the caller's current device as it was
     }
 };
 ScratchCache g_scratch;
@@ -87,6 +92,9 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
     const size_t R = (size_t)S * (size_t)n_rows;
     if (R > 0x7fffffffu) { set_error("mcl_objective: too many replicas"); return MCL_ERR_ARG; }
 
+    // One call at a time: concurrent callers would run kernels in the same cached slab (and a larger request
+    // would free it under the other call).  Documented in mcl_b200.h.
+    std::lock_guard<std::mutex> call_lock(g_scratch.call_mu);
     std::vector<mcl_replica> reps(R);
     std::vector<mcl_segment> segs(lab->rows, lab->rows + n_rows);
     for (int k = 0; k < n_rows; k++) {

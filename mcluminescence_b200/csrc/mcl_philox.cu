@@ -101,6 +101,12 @@ __device__ __forceinline__ float warp_min_f32(float v)
     asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
     return r;
 }
+__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v)
+{
+    uint32_t r;
+    asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
 // u32 -> uniform on [2^-24, 1 - 2^-24] (exact): one LEA.HI + one FADD, no conversion instruction
 __device__ __forceinline__ float u01(uint32_t r) { return __uint_as_float((r >> 9) | 0x3f800000u) - 0.99999994f; }
 
@@ -599,8 +605,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     const size_t rec_base = (size_t)r * (size_t)p.max_steps;
     const bool trace = (p.event != nullptr) || (p.n_e != nullptr) || (p.t != nullptr);
     // histogram
-    const bool hist_on = p.hist.n_bins > 0;
-    const int hgroup = (hist_on && p.hist_group) ? p.hist_group[r] : 0;
+    const int hgroup = (p.hist.n_bins > 0 && p.hist_group) ? p.hist_group[r] : 0;
+    // rows are validated on the host (plan_layout); a replica whose rows do not fit writes no histogram at all
+    const bool hist_on = p.hist.n_bins > 0 && hgroup >= 0 && hgroup + rp.seg_count <= p.hist.n_groups;
 
     auto flush_records = [&](int count) {       // warp 0 only; count <= 32 records ending at rec_i
         if (!trace || warp != 0) return;
@@ -624,7 +631,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         const float A_opt = lab ? 0.0f : (float)S.A_opt;
         double t_cur = 0.0;
         // histogram cursor for this leg
-        const int hrow = hist_on ? (hgroup * rp.seg_count + sg) : 0;
+        const int hrow = hist_on ? (hgroup + sg) : 0;             // leg sg -> row hist_group[r] + sg (mcl_run validates the range)
         int hbin_next = 0;        // next bin whose left edge has not been passed yet
 
         // Histogram axis of this leg.  Bin edges are visited in order, so the cursor (hbin_next, hedge_next)
@@ -776,10 +783,10 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 else          { if (has_cb) pair_loop(std::true_type{}, std::false_type{}); else pair_loop(std::false_type{}, std::false_type{}); }
                 // warp argmin -> one row per warp
                 {
+                    // ties on the FP32 clock go to the SMALLEST SLOT (a thread keeps its lowest slot already: ascending
+                    // chunks, strict <), so the winner does not depend on which thread owns which slot -- i.e. on NT
                     float wv = warp_min_f32(best);
-                    unsigned m = __ballot_sync(0xffffffffu, best == wv);
-                    int src = m ? (__ffs(m) - 1) : 0;
-                    int ws_ = __shfl_sync(0xffffffffu, bslot, src);
+                    int ws_ = (int)warp_min_u32(best == wv ? (uint32_t)bslot : 0xffffffffu);     // -1 when the warp has no clock
                     __syncwarp();
                     if (lane == 0) red_row[par][warp] = make_int4(__float_as_int(wv), ws_, ws_ >= 0 ? (int)near[ws_] : -1, 0);
                 }
@@ -807,10 +814,17 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     const float v = __int_as_float(row.x);
                     const int s = row.y, hh = row.z;
                     vmin = warp_min_f32(v);
-                    unsigned m = __ballot_sync(0xffffffffu, v == vmin);
-                    const int src = m ? (__ffs(m) - 1) : 0;
-                    smin = __shfl_sync(0xffffffffu, s, src);
-                    hmin = __shfl_sync(0xffffffffu, hh, src);
+                    if (sizeof(NearT) == 2) {
+                        // slot < 2^15 and hole < 2^16: one packed minimum gives the smallest tied slot and its hole
+                        const uint32_t key = (v == vmin && s >= 0) ? (((uint32_t)s << 16) | ((uint32_t)hh & 0xffffu)) : 0xffffffffu;
+                        const uint32_t k = warp_min_u32(key);
+                        smin = k == 0xffffffffu ? -1 : (int)(k >> 16);
+                        hmin = k == 0xffffffffu ? -1 : (int)(k & 0xffffu);
+                    } else {
+                        smin = (int)warp_min_u32(v == vmin ? (uint32_t)s : 0xffffffffu);
+                        const unsigned m = __ballot_sync(0xffffffffu, v == vmin && s == smin);
+                        hmin = __shfl_sync(0xffffffffu, hh, m ? (__ffs(m) - 1) : 0);
+                    }
                 }
                 // ---------------- filling clock (tl_trap_lab.py:53-60) and dt (simulate.py:58-60)
                 // Without a dose the clock is exponential(1e20 s) >= -ln(1 - 2^-24) * 1e20 = 5.96e12 s: it can only matter (the
@@ -1163,6 +1177,37 @@ static inline uint64_t mix64(uint64_t z)
 }  // namespace
 
 int philox_max_slots() { return 24000; }
+
+// Test hook (include/mcl_b200.h): the kernel's exponential draw -lg2(u01(word)) for given Philox words, so that the
+// small-waiting-time tail of the SFU logarithm can be pinned against float64 on the device it runs on.
+namespace {
+__global__ void exp_draw_kernel(const uint32_t *w, int n, float *neg_lg2_u, float *lg2_of_that)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float e2 = -lg2_fast(u01(w[i]));
+    neg_lg2_u[i] = e2;
+    lg2_of_that[i] = lg2_fast(e2);
+}
+}  // namespace
+
+extern "C" int mcl_debug_exp_draws(const uint32_t *words, int32_t n, float *neg_lg2_u, float *lg2_of_that)
+{
+    if (!words || n <= 0 || !neg_lg2_u || !lg2_of_that) { set_error("mcl_debug_exp_draws: null argument"); return MCL_ERR_ARG; }
+    uint32_t *dw = nullptr; float *da = nullptr, *db = nullptr;
+    int rc = MCL_OK;
+    if (cudaMalloc(&dw, sizeof(uint32_t) * (size_t)n) != cudaSuccess || cudaMalloc(&da, sizeof(float) * (size_t)n) != cudaSuccess ||
+        cudaMalloc(&db, sizeof(float) * (size_t)n) != cudaSuccess) { set_error("mcl_debug_exp_draws: cudaMalloc failed"); rc = MCL_ERR_ALLOC; }
+    if (rc == MCL_OK) {
+        cudaMemcpy(dw, words, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice);
+        exp_draw_kernel<<<(n + 255) / 256, 256>>>(dw, n, da, db);
+        cudaMemcpy(neg_lg2_u, da, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaMemcpy(lg2_of_that, db, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("mcl_debug_exp_draws: %s", cudaGetErrorString(e)); rc = MCL_ERR_CUDA; }
+    }
+    cudaFree(dw); cudaFree(da); cudaFree(db);
+    return rc;
+}
 
 #ifdef MCL_PROFILE_SKEW
 extern "C" int mcl_debug_prof(unsigned long long *out, int reset)

@@ -84,7 +84,7 @@ def c3(replicas_per_dose: int = 256, n_bins: int = 800):
         legs.append(dict(T_start=0.0, T_rate=1.0, duration=800.0, dose_rate=0.0, dt_cap=1.0, A_opt=0.0))
         sl = slice(d * replicas_per_dose, (d + 1) * replicas_per_dose)
         reps["seg_begin"][sl], reps["seg_count"][sl] = 2 * d, 2
-        group[sl] = d
+        group[sl] = 2 * d                       # row of the replica's first leg; leg sg writes row 2 d + sg
     hist = HistSpec(axis=AXIS_TEMP, n_bins=n_bins, lo=0.0, hi=800.0, n_groups=20)
     return dict(name=f"C3 dose response: 10 doses x {replicas_per_dose} replicas, irradiation then TL, N_e=2000",
                 replicas=reps, segments=_segments(*legs), max_steps=40000, hist=hist, hist_group=group)
