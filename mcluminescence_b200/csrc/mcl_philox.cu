@@ -1,7 +1,7 @@
 // mcl_philox.cu -- native throughput kernel of the trapped-charge kinetics loop (sm_100a).
 //
 // One CTA (NT = 32..512 threads) per replica; one electron per shared-memory slot; one Philox call serves a chunk of
-// four slots when the two tunnelling channels are identical (no selector needed), two slots otherwise.
+// four slots (top 23 bits of a word: the exponential draw; its 9 low bits: the tunnelling-channel selector).
 // What one step does (reference src/class/simulate.py:51-92, tl_trap_lab.py:90-108):
 //   1. SWEEP.  Every alive electron i draws a selector and an exponential and forms its waiting time
 //        wait_i = E_i / (k_cb + b*exp(-E_loc/kT - alpha*r_i))          (engine.py:65-77, tl_trap_lab.py:51)
@@ -43,7 +43,7 @@ namespace {
 
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
-constexpr uint32_t DOM_STEP = 0u, DOM_SCALAR = 1u, DOM_SEED_E = 2u, DOM_SEED_H = 3u, DOM_STEP1 = 4u;
+constexpr uint32_t DOM_SCALAR = 1u, DOM_SEED_E = 2u, DOM_SEED_H = 3u, DOM_STEP1 = 4u, DOM_SEL = 5u;
 #ifndef MCL_SCAN_UNROLL
 #define MCL_SCAN_UNROLL 4
 #endif
@@ -91,6 +91,23 @@ __device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32
         uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k[2 * r + 1];
         c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
     }
+}
+
+// Rare path of the channel selector (a 9-bit tie, probability 2^-9 per electron-step): the four words that settle the
+// ties of one chunk.  Out of line, with the round keys rebuilt from the two key words, so that the sweep carries
+// neither its code nor its registers.
+__device__ __noinline__ uint4 philox_tie_words(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+#pragma unroll 1
+    for (int r = 0; r < 10; r++) {
+        unsigned long long p0 = (unsigned long long)PHILOX_M0 * c0;
+        unsigned long long p1 = (unsigned long long)PHILOX_M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += PHILOX_W0; k1 += PHILOX_W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
 }
 
 __device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -585,9 +602,14 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     const float lb = (float)log2(rp.b), ls = (float)log2(rp.s);
     const float eb1 = (float)(rp.E_loc_1 * L2E / rp.k_b), eb2 = (float)(rp.E_loc_2 * L2E / rp.k_b);
     const float ecb = (float)(rp.E_cb * L2E / rp.k_b);
-    // U < Retrap  <=>  r < thr ; Retrap >= 1 / <= 0 handled by collapsing the two channels
+    // Channel selector U < Retrap (engine.py:72), drawn from the 9 low bits the exponential draw leaves unused in every
+    // Philox word (u01 keeps the top 23): sel9 < T9 -> channel 2, sel9 > T9 -> channel 1, sel9 == T9 -> one more word
+    // against the remainder (probability 2^-9, settled by a second call for that chunk only).
+    // P(channel 2) = T9/512 + frac/512 = Retrap, exact to 2^-41.  Retrap >= 1 / <= 0 collapse the two channels.
     const bool one_ch_2 = rp.Retrap >= 1.0, one_ch_1 = rp.Retrap <= 0.0;
-    const uint32_t thr = (one_ch_1 || one_ch_2) ? 0u : (uint32_t)(rp.Retrap * 4294967296.0);
+    const double sel_scaled = (one_ch_1 || one_ch_2) ? 0.0 : rp.Retrap * 512.0;
+    const uint32_t sel_T9 = (uint32_t)sel_scaled;
+    const uint32_t sel_frac = (uint32_t)fmin((sel_scaled - (double)sel_T9) * 4294967296.0, 4294967295.0);
     const float cr_far = bnd_s * 1.7320508f;        // no electron-hole distance exceeds the box diagonal
 
     const bool lab = rp.protocol != MCL_PROTO_SIMULATE;
@@ -708,76 +730,66 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 auto pair_loop = [&](auto with_cb, auto one_channel) {
                     constexpr bool CB = decltype(with_cb)::value;
                     constexpr bool ONE = decltype(one_channel)::value;     // both tunnelling channels identical
-                    if constexpr (ONE) {
-                        // Identical channels: the selector draw cannot change anything, so no word is spent on it.  One
-                        // Philox call serves the FOUR slots of a chunk (word k -> slot 4b + k); MCL_ONE_CHAINS chunks of
-                        // the same owner per iteration keep that many independent Philox chains in flight.
-                        const float4 *cr4 = reinterpret_cast<const float4 *>(cr);
-                        auto chunks = [&](auto n_chains, int b0) {
-                            constexpr int NCH = decltype(n_chains)::value;
-                            float cs[NCH][4];
-                            uint32_t w[NCH][4];
+                    // One Philox call serves the FOUR slots of a chunk (word k -> slot 4b + k): the top 23 bits of a word are
+                    // the electron's exponential draw, its 9 low bits the channel selector (not looked at when the channels
+                    // are identical).  MCL_ONE_CHAINS chunks of the same owner per iteration keep that many independent
+                    // Philox chains in flight.
+                    const float4 *cr4 = reinterpret_cast<const float4 *>(cr);
+                    auto chunks = [&](auto n_chains, int b0) {
+                        constexpr int NCH = decltype(n_chains)::value;
+                        float cs[NCH][4];
+                        uint32_t w[NCH][4];
 #pragma unroll
-                            for (int q = 0; q < NCH; q++) {
-                                const int b = b0 + q * NT;
-                                const float4 cq = cr4[b];
-                                cs[q][0] = cq.x; cs[q][1] = cq.y; cs[q][2] = cq.z; cs[q][3] = cq.w;
-                                w[q][0] = (uint32_t)b; w[q][1] = (uint32_t)rec_i; w[q][2] = rid_lo; w[q][3] = rid_hi | (DOM_STEP1 << 28);
-                            }
+                        for (int q = 0; q < NCH; q++) {
+                            const int b = b0 + q * NT;
+                            const float4 cq = cr4[b];
+                            cs[q][0] = cq.x; cs[q][1] = cq.y; cs[q][2] = cq.z; cs[q][3] = cq.w;
+                            w[q][0] = (uint32_t)b; w[q][1] = (uint32_t)rec_i; w[q][2] = rid_lo; w[q][3] = rid_hi | (DOM_STEP1 << 28);
+                        }
 #pragma unroll
-                            for (int q = 0; q < NCH; q++) philox4x32_10(w[q][0], w[q][1], w[q][2], w[q][3], K);
+                        for (int q = 0; q < NCH; q++) philox4x32_10(w[q][0], w[q][1], w[q][2], w[q][3], K);
 #pragma unroll
-                            for (int q = 0; q < NCH; q++) {
+                        for (int q = 0; q < NCH; q++) {
+                            uint32_t ch2 = 0u;                             // bit k: slot k of the chunk uses channel 2
+                            if (!ONE) {
+                                uint32_t tie = 0u;
 #pragma unroll
                                 for (int k = 0; k < 4; k++) {
-                                    const float le = lg2_fast(-lg2_fast(u01(w[q][k])));
-                                    float l;
-                                    if (CB) {
-                                        // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
-                                        const float a = A1 - cs[q][k];
-                                        const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
-                                        l = (le - kk) + (cs[q][k] - cs[q][k]);
-                                    } else {
-                                        l = le + cs[q][k];              // the uniform prefactor A1 is subtracted after the loop
-                                    }
-                                    if (l < best) { best = l; bslot = 4 * (b0 + q * NT) + k; }
+                                    const uint32_t sel = w[q][k] & 0x1ffu;
+                                    ch2 |= (sel < sel_T9) ? (1u << k) : 0u;
+                                    tie |= (sel == sel_T9) ? (1u << k) : 0u;
+                                }
+                                if (tie && sel_frac) {                     // 2^-9 per slot, and only when Retrap * 512 has a remainder
+                                    const uint4 tw = philox_tie_words((uint32_t)(b0 + q * NT), (uint32_t)rec_i, rid_lo, rid_hi | (DOM_SEL << 28), K.k[0], K.k[1]);
+                                    const uint32_t t4[4] = {tw.x, tw.y, tw.z, tw.w};
+#pragma unroll
+                                    for (int k = 0; k < 4; k++) ch2 |= (((tie >> k) & 1u) && t4[k] < sel_frac) ? (1u << k) : 0u;
                                 }
                             }
-                        };
-                        int b0 = tid;
-                        for (; b0 + (MCL_ONE_CHAINS - 1) * NT < n_chunks; b0 += MCL_ONE_CHAINS * NT)
-                            chunks(std::integral_constant<int, MCL_ONE_CHAINS>{}, b0);
-                        for (; b0 < n_chunks; b0 += NT) chunks(std::integral_constant<int, 1>{}, b0);       // tail: no wasted calls
-                        if (!CB) best -= A1;
-                    } else {
-                        for (int b = tid; b < n_chunks; b += NT) {
-                            float cs[SPC];
-                            const float4 cq = reinterpret_cast<const float4 *>(cr)[b];
-                            cs[0] = cq.x; cs[1] = cq.y; cs[2] = cq.z; cs[3] = cq.w;
-                            float l[SPC];
 #pragma unroll
-                            for (int i = 0; i < PPC; i++) {
-                                uint32_t c0 = (uint32_t)(PPC * b + i), c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);
-                                philox4x32_10(c0, c1, c2, c3, K);
-                                // the selector draws (c0, c2) pick the channel
-                                const float a0 = ((c0 < thr) ? A2 : A1) - cs[2 * i];
-                                const float a1 = ((c2 < thr) ? A2 : A1) - cs[2 * i + 1];
-                                const float le0 = lg2_fast(-lg2_fast(u01(c1)));
-                                const float le1 = lg2_fast(-lg2_fast(u01(c3)));
+                            for (int k = 0; k < 4; k++) {
+                                const float le = lg2_fast(-lg2_fast(u01(w[q][k])));
+                                const float Ak = (!ONE && ((ch2 >> k) & 1u)) ? A2 : A1;
+                                float l;
                                 if (CB) {
-                                    const float k0 = fmaxf(a0, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a0 - g)));
-                                    const float k1 = fmaxf(a1, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a1 - g)));
-                                    l[2 * i] = (le0 - k0) + (cs[2 * i] - cs[2 * i]);
-                                    l[2 * i + 1] = (le1 - k1) + (cs[2 * i + 1] - cs[2 * i + 1]);
+                                    // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
+                                    const float a = Ak - cs[q][k];
+                                    const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
+                                    l = (le - kk) + (cs[q][k] - cs[q][k]);
+                                } else if (ONE) {
+                                    l = le + cs[q][k];                     // the uniform prefactor A1 is subtracted after the loop
                                 } else {
-                                    l[2 * i] = le0 - a0;
-                                    l[2 * i + 1] = le1 - a1;
+                                    l = (le + cs[q][k]) - Ak;
                                 }
+                                if (l < best) { best = l; bslot = 4 * (b0 + q * NT) + k; }
                             }
-#pragma unroll
-                            for (int i = 0; i < SPC; i++) if (l[i] < best) { best = l[i]; bslot = SPC * b + i; }
                         }
-                    }
+                    };
+                    int b0 = tid;
+                    for (; b0 + (MCL_ONE_CHAINS - 1) * NT < n_chunks; b0 += MCL_ONE_CHAINS * NT)
+                        chunks(std::integral_constant<int, MCL_ONE_CHAINS>{}, b0);
+                    for (; b0 < n_chunks; b0 += NT) chunks(std::integral_constant<int, 1>{}, b0);       // tail: no wasted calls
+                    if (ONE && !CB) best -= A1;
                 };
                 if (A1 == A2) { if (has_cb) pair_loop(std::true_type{}, std::true_type{}); else pair_loop(std::false_type{}, std::true_type{}); }
                 else          { if (has_cb) pair_loop(std::true_type{}, std::false_type{}); else pair_loop(std::false_type{}, std::false_type{}); }

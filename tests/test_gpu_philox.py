@@ -226,3 +226,28 @@ def test_decay_follows_the_nearest_neighbour_integral(gpu, T_c, A_opt):
     fin = engine.run_replicas(reps, segs, steps, seed=int(5 + T_c), trace=False, sync=True)
     fin.raise_on_error()
     assert np.array_equal(fin.final_n_e, out.final_n_e)
+
+
+@pytest.mark.parametrize("retrap", [3.5 / 512.0, 0.1, 0.5, 0.77])
+def test_channel_selector_matches_oracle_across_retrap(gpu, retrap):
+    """The channel selector U < Retrap (engine.py:72) comes from the 9 spare low bits of the word that carries the
+    exponential draw, ties settled by one more word: exact for every Retrap.  Channel 2 (E_loc_2 = 1.0 eV) tunnels
+    ~80x faster than channel 1 at 250 degC, so the decay rate is nearly proportional to P(channel 2): 3.5/512 is the
+    case in which one seventh of that probability comes from the tie-break word, 0.5 the one without any tie-break."""
+    from mcluminescence_b200 import engine
+    from oracle import mcl_oracle as mo
+    overrides = list(CASES["iso_two_channel"][0])
+    overrides[-1] = f"physics_fp.Retrap={retrap!r}"
+    R = 512
+    reps, segs, steps = ensemble_tables(overrides, R)
+    out = engine.run_replicas(reps, segs, steps, seed=int(retrap * 1e6) + 3, sync=True)
+    out.raise_on_error()
+    ref = mo.run(reps, segs, steps, seed=4321, parallel=True)
+    assert ref.rc == 0
+    grid = np.geomspace(1, 900, 10)
+    g = stats(out.event, out.n_e, out.t, out.steps_used, grid, int(reps['n_e0'][0]))
+    o = stats(ref.event, ref.n_e, ref.t, ref.steps_used, grid, int(reps['n_e0'][0]))
+    assert_means_agree(g[0], o[0], f"Retrap={retrap}: events per replica")
+    for k in range(len(grid)):
+        assert_means_agree(g[2][:, k], o[2][:, k], f"Retrap={retrap}: n_e(t={grid[k]:.3g})")
+    assert g[0].mean() > 3.0                      # the case is informative: several events per replica
