@@ -167,6 +167,8 @@ int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uint64_t seed,
  * after another.  mcl_release_scratch frees the slabs of every device (waiting for a running call)
  * and leaves the caller's current device unchanged. */
 void mcl_release_scratch(void);
+/* Device time (ms, CUDA events around the kernel launch) of this thread's last mcl_objective call. */
+float mcl_objective_last_kernel_ms(void);
 
 /* Issue-rate microbenchmarks for the roofline denominators (SFU, FP32 FMA, INT32 multiply-add,
  * LOP3), measured on the current device.  Results in giga lane-ops per second. */

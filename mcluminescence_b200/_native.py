@@ -14,7 +14,7 @@ ABI_VERSION = 1
 
 EXPORTS = (
     "mcl_abi_version", "mcl_last_error", "mcl_workspace_bytes", "mcl_run", "mcl_run_host",
-    "mcl_device_peaks", "mcl_objective", "mcl_release_scratch", "mcl_debug_exp_draws",
+    "mcl_device_peaks", "mcl_objective", "mcl_release_scratch", "mcl_debug_exp_draws", "mcl_objective_last_kernel_ms",
 )
 
 
@@ -107,6 +107,7 @@ def load():
         L.mcl_objective.restype = C.c_int
         L.mcl_objective.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Lab), C.c_uint64, C.c_uint64,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcl_objective_last_kernel_ms.restype = C.c_float
     L.mcl_debug_exp_draws.restype = C.c_int
     L.mcl_debug_exp_draws.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     if L.mcl_abi_version() != ABI_VERSION:

@@ -22,6 +22,7 @@ struct Layout {
     size_t off_rep, off_seg, off_obs, off_grp, off_slabs, total;
     size_t stride;
     int cap_e, cap_h;
+    bool any_dose;
 };
 
 static int plan_layout(const mcl_run_args *a, Layout *L)
@@ -60,8 +61,9 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
     }
     L->cap_e = ne_max + 8 + seg_max;
     if (a->mode == MCL_MODE_REPLAY) L->cap_h = nh_max + L->cap_e + 8;
-    else L->cap_h = nh_max + (any_dose ? nh_max + ne_max : 0) + 64 + seg_max;
-    L->stride = a->mode == MCL_MODE_REPLAY ? replay_ws_stride(L->cap_e, L->cap_h) : philox_ws_stride(L->cap_e, L->cap_h);
+    else L->cap_h = nh_max + (any_dose ? 2 * ne_max + kFillExtra : 0) + 64 + seg_max;     // see kFillExtra (regrid)
+    L->any_dose = any_dose;
+    L->stride = a->mode == MCL_MODE_REPLAY ? replay_ws_stride(L->cap_e, L->cap_h) : philox_ws_stride(L->cap_e, L->cap_h, any_dose);
     size_t o = 0;
     L->off_rep = o; o = align_up(o + sizeof(mcl_replica) * (size_t)a->n_replicas, 256);
     L->off_seg = o; o = align_up(o + sizeof(mcl_segment) * (size_t)a->n_segments, 256);
@@ -78,7 +80,7 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
         if (_e != cudaSuccess) { set_error("%s: %s", #x, cudaGetErrorString(_e)); return MCL_ERR_CUDA; } \
     } while (0)
 
-static int run_device(const mcl_run_args *a)
+static int run_device(const mcl_run_args *a, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr)
 {
     Layout L;
     int rc = plan_layout(a, &L);
@@ -116,11 +118,15 @@ static int run_device(const mcl_run_args *a)
         p.hist_occ = (unsigned long long *)a->hist_occ;
         p.hist_occ_sq = (unsigned long long *)a->hist_occ_sq;
     }
-    p.ws = ws + L.off_slabs; p.ws_stride = L.stride; p.cap_e = L.cap_e; p.cap_h = L.cap_h;
+    p.ws = ws + L.off_slabs; p.ws_stride = L.stride; p.cap_e = L.cap_e; p.cap_h = L.cap_h; p.with_regrid = L.any_dose ? 1 : 0;
+    if (ev0) cudaEventRecord(ev0, st);
     cudaError_t e = a->mode == MCL_MODE_REPLAY ? launch_replay(p, st) : launch_philox(p, st, 0);
+    if (ev1) cudaEventRecord(ev1, st);
     if (e != cudaSuccess) { set_error("kernel launch: %s", cudaGetErrorString(e)); return MCL_ERR_CUDA; }
     return MCL_OK;
 }
+
+int mcl_run_timed(const mcl_run_args *a, void *ev0, void *ev1) { return run_device(a, (cudaEvent_t)ev0, (cudaEvent_t)ev1); }
 
 }  // namespace mcl
 

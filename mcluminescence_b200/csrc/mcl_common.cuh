@@ -32,15 +32,21 @@ struct LaunchParams {
     unsigned char *ws;
     size_t ws_stride;
     int32_t cap_e, cap_h;        // per-replica element capacities inside the scratch
+    int32_t with_regrid;         // the slabs carry the regrid scratch (some replica of the launch has a dosed leg)
 };
 
+// Fill-region slots beyond N_e: a fill that finds N_e + kFillExtra of them in use folds them into the cell grid first, so a
+// replica never needs more than n_h0 + 2 N_e + kFillExtra hole slots (alive holes <= n_h0 + N_e at any time).
+constexpr int kFillExtra = 64;
+
 void set_error(const char *fmt, ...);
+int mcl_run_timed(const mcl_run_args *a, void *ev0, void *ev1);   // mcl_run with CUDA events recorded around the kernel launch
 
 // kernels' host launchers (defined in the .cu files)
 cudaError_t launch_replay(const LaunchParams &p, cudaStream_t stream);
 cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int max_slots);
 size_t replay_ws_stride(int cap_e, int cap_h);
-size_t philox_ws_stride(int cap_e, int cap_h);
+size_t philox_ws_stride(int cap_e, int cap_h, bool with_regrid);
 int philox_max_slots();       // largest per-replica electron capacity the block kernel supports
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

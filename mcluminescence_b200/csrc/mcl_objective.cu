@@ -75,6 +75,7 @@ struct ScratchCache {
     }
 };
 ScratchCache g_scratch;
+thread_local float g_last_kernel_ms = 0.f;
 
 }  // namespace
 
@@ -146,17 +147,26 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
     void *scratch = g_scratch.get(need);
     if (!scratch) { set_error("mcl_objective: cudaMalloc(workspace %zu) failed", need); return MCL_ERR_ALLOC; }
     a.workspace = scratch; a.workspace_bytes = need;
-    int rc = mcl_run(&a);
-    if (rc) return rc;
+    // kernel time of this call (H2D of the tables excluded), for the benchmark's roofline line
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    const bool timed = cudaEventCreate(&ev0) == cudaSuccess && cudaEventCreate(&ev1) == cudaSuccess;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = mcl_run_timed(&a, timed ? (void *)ev0 : nullptr, timed ? (void *)ev1 : nullptr);
+    if (rc) { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); return rc; }
 
     std::vector<int32_t> final_n(R), status(R), obs_n(obs.size());
     std::vector<int64_t> est(R);
-    cudaStream_t st = (cudaStream_t)stream;
     cudaMemcpyAsync(final_n.data(), d_final.p, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(status.data(), d_status.p, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(est.data(), d_esteps.p, sizeof(int64_t) * R, cudaMemcpyDeviceToHost, st);
     if (iso) cudaMemcpyAsync(obs_n.data(), d_obs.p, sizeof(int32_t) * obs.size(), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
+    if (timed) {
+        float ms = 0.f;
+        if (e == cudaSuccess && cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) g_last_kernel_ms = ms;
+    }
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
     if (e != cudaSuccess) { set_error("mcl_objective: %s", cudaGetErrorString(e)); return MCL_ERR_CUDA; }
 
     int64_t total = 0;
@@ -187,3 +197,4 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
 }
 
 extern "C" void mcl_release_scratch(void) { g_scratch.release(); }
+extern "C" float mcl_objective_last_kernel_ms(void) { return g_last_kernel_ms; }

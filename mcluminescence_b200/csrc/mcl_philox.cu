@@ -78,6 +78,13 @@ struct Cfg {
     size_t off_holes;  // byte offset of the hole table inside the slab (16-byte aligned)
     size_t off_cand;   // byte offset of the candidate lists inside the slab
     int fast;          // 1: legs that qualify run the specialised step loop (0: always the general one; same results)
+    size_t off_hpos2;  // byte offset (global slab) of the second hole table used by a regrid
+    size_t off_hmap;   // byte offset (global slab) of the old-slot -> new-slot table of a regrid
+    int fill_extra;    // fill-region slots beyond N_e: a fill that finds N_e + fill_extra of them in use regrids first
+    int has_regrid;    // the slab has the regrid scratch (launches with a dosed leg somewhere)
+    int relist;        // 1: a dose-free simulate leg that follows fills regrids and rebuilds the candidate lists
+    // shared-memory slab (small boxes): word offsets from the start of dynamic shared memory
+    int sm_hpos, sm_exyz, sm_cstart, sm_cfill;
 };
 
 __device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
@@ -96,7 +103,8 @@ __device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32
 // Rare path of the channel selector (a 9-bit tie, probability 2^-9 per electron-step): the four words that settle the
 // ties of one chunk.  Out of line, with the round keys rebuilt from the two key words, so that the sweep carries
 // neither its code nor its registers.
-__device__ __noinline__ uint4 philox_tie_words(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+__device__ __noinline__ bool philox_tie_is_ch2(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                               int k, uint32_t sel_frac)
 {
 #pragma unroll 1
     for (int r = 0; r < 10; r++) {
@@ -107,7 +115,8 @@ __device__ __noinline__ uint4 philox_tie_words(uint32_t c0, uint32_t c1, uint32_
         c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
         k0 += PHILOX_W0; k1 += PHILOX_W1;
     }
-    return make_uint4(c0, c1, c2, c3);
+    const uint32_t w = k == 0 ? c0 : (k == 1 ? c1 : (k == 2 ? c2 : c3));
+    return w < sel_frac;
 }
 
 __device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -143,6 +152,12 @@ struct Holes {
     int G, n_h0, n_slots;        // n_slots = high-water mark including the fill region
     float inv_w, w;
 };
+
+__device__ __forceinline__ int cell_index(const Holes &H, float x, float y, float z)
+{
+    const int cx = min(H.G - 1, (int)(x * H.inv_w)), cy = min(H.G - 1, (int)(y * H.inv_w)), cz = min(H.G - 1, (int)(z * H.inv_w));
+    return (cx * H.G + cy) * H.G + cz;
+}
 
 // Warp-cooperative nearest alive hole of (x,y,z).  Returns (bits(d2) << 32 | slot) to all lanes.
 __device__ unsigned long long warp_nearest(const Holes &H, float x, float y, float z, int lane, int exclude = -1)
@@ -398,7 +413,10 @@ __device__ __noinline__ void seed_candidate_lists_call(const Holes &H, const int
     seed_candidate_lists_impl<NearT>(H, e_start, ex, ey, ez, cand_d, cand_j, cr, near, n_cells, warp, lane, NW);
 }
 
-template <int NT, int MINB, typename NearT, int PPC>
+// SLAB_SMEM: the hole table, the cell tables and the electron coordinates of the replica live in shared memory instead of
+// its HBM slab (small boxes -- the Optimizer path: every nearest-hole search is then a handful of shared-memory reads
+// instead of dependent L2 / HBM round trips).  Same algorithm, same results.
+template <int NT, int MINB, typename NearT, int PPC, bool SLAB_SMEM = false>
 __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, const RoundKeys K, const Cfg cfg)
 {
     constexpr int NW = NT / 32;
@@ -449,8 +467,17 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     float *ex = reinterpret_cast<float *>(ws), *ey = ex + ce, *ez = ex + 2 * ce;
     float4 *hpos = reinterpret_cast<float4 *>(ws + cfg.off_holes);    // [cap_h] (x, y, z, original index)
     int *cell_start = reinterpret_cast<int *>(hpos + ch);             // [cap_cells]
-    int *cell_fill = cell_start + cfg.cap_cells;                      // [cap_cells] init only
+    int *cell_fill = cell_start + cfg.cap_cells;                      // [cap_cells] seeding / regrid only
     int *e_id_buf = cell_fill + cfg.cap_cells;                        // [cap_e] seeding only
+    if (SLAB_SMEM) {
+        uint32_t *sm = reinterpret_cast<uint32_t *>(smem_raw);
+        hpos = reinterpret_cast<float4 *>(sm + cfg.sm_hpos);
+        ex = reinterpret_cast<float *>(sm + cfg.sm_exyz); ey = ex + ce; ez = ex + 2 * ce;
+        cell_start = reinterpret_cast<int *>(sm + cfg.sm_cstart);
+        cell_fill = reinterpret_cast<int *>(sm + cfg.sm_cfill);
+    }
+    float4 *hpos2 = reinterpret_cast<float4 *>(ws + cfg.off_hpos2);   // [cap_h] regrid only
+    int *hmap = reinterpret_cast<int *>(ws + cfg.off_hmap);           // [cap_h] regrid only
     float4 *cand_d = reinterpret_cast<float4 *>(ws + cfg.off_cand);   // [cap_e] cr of the KC nearest initial holes
     NearT *cand_j = reinterpret_cast<NearT *>(cand_d + ce);           // [cap_e][KC] their slots (NEAR_DEAD = none)
 
@@ -463,7 +490,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     int status = MCL_OK;
     const float core_s = (float)(rp.side * rp.alpha * L2E);
     const float bnd_s = (float)(rp.side * rp.boundary_factor * rp.alpha * L2E);
-    const int n_h0 = rp.n_h0;
+    const int n_h0 = rp.n_h0;         // INITIAL holes; H.n_h0 is the size of the grid region (changes in a regrid)
     int n_e = rp.n_e0;
     if (n_e > cfg.cap_slots - 4 || n_e > p.cap_e || n_h0 > p.cap_h) status = MCL_ERR_CAPACITY;
     if (n_e > 0 && n_h0 <= 0) status = MCL_ERR_NOHOLES;
@@ -489,11 +516,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             philox4x32_10(c0, c1, c2, c3, K);
             x = u01(c0) * bnd_s; y = u01(c1) * bnd_s; z = u01(c2) * bnd_s;
         };
-        auto cell_of = [&](float x, float y, float z) {
-            int cx = min(H.G - 1, (int)(x * H.inv_w)), cy = min(H.G - 1, (int)(y * H.inv_w)),
-                cz = min(H.G - 1, (int)(z * H.inv_w));
-            return (cx * H.G + cy) * H.G + cz;
-        };
+        auto cell_of = [&](float x, float y, float z) { return cell_index(H, x, y, z); };
         for (int j = tid; j < n_h0; j += NT) {
             float x, y, z; hole_pos(j, x, y, z);
             atomicAdd(&cell_fill[cell_of(x, y, z)], 1);
@@ -610,6 +633,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     const double sel_scaled = (one_ch_1 || one_ch_2) ? 0.0 : rp.Retrap * 512.0;
     const uint32_t sel_T9 = (uint32_t)sel_scaled;
     const uint32_t sel_frac = (uint32_t)fmin((sel_scaled - (double)sel_T9) * 4294967296.0, 4294967295.0);
+    const uint32_t sel_tie = sel_frac ? sel_T9 : 0xffffu;           // no remainder: sel9 == T9 is plain channel 1
     const float cr_far = bnd_s * 1.7320508f;        // no electron-hole distance exceeds the box diagonal
 
     const bool lab = rp.protocol != MCL_PROTO_SIMULATE;
@@ -619,6 +643,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     int n_slots = n_e;             // electron slots in use (alive or tombstoned)
     int n_fill_alive = 0;          // alive holes in the fill region
     bool ever_filled = false;
+    bool lists_valid = true;       // the candidate lists name the K nearest of ALL holes that were ever alive since they were built
     bool draws_valid = false;      // stepdraw holds the block of 32 steps that contains rec_i
     int rec_i = 0;
     long long esteps = 0;
@@ -642,6 +667,108 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             if (p.t) p.t[q] = rec_t[lane];
         }
         __syncwarp();
+    };
+
+    // ---------------- regrid: every alive hole (initial or added by a fill) is re-binned into a fresh cell grid and the
+    // hole slots are renumbered densely in cell order; the fill region is empty afterwards.  Called (by all threads)
+    // when a fill finds N_e + fill_extra fill-region slots in use -- which bounds the hole capacity a replica needs at
+    // n_h0 + 2 N_e + fill_extra whatever its history -- and at the start of a dose-free leg that follows fills, before
+    // the candidate lists are rebuilt.  The trigger depends on the replica's own state only, never on the launch.
+    // Cached nearest holes stay what they were (the reference's cache is stale by design, engine.py:147-152); only
+    // their slot numbers change.  alive holes - n_e is invariant (pairs are added and removed together).
+    const int fill_cap = max(4, rp.N_e + cfg.fill_extra);
+    bool can_regrid = false;       // only replicas with a dosed leg regrid (the launch then has the scratch for it)
+    for (int sg = 0; sg < rp.seg_count; sg++) can_regrid |= p.segments[rp.seg_begin + sg].dose_rate != 0.0;
+    can_regrid = can_regrid && cfg.has_regrid;
+    auto regrid = [&]() {
+        cta_sync<NT>();
+        const int n_old = H.n_slots;
+        const int n_alive = n_h0 - rp.n_e0 + n_e;
+        H.G = max(1, min(cfg.g_max, (int)cbrtf((float)n_alive * (1.0f / 3.0f))));
+        H.w = bnd_s / (float)H.G; H.inv_w = (float)H.G / bnd_s;
+        const int nc = H.G * H.G * H.G;
+        for (int c = tid; c <= nc; c += NT) { cell_start[c] = 0; cell_fill[c] = 0; }
+        cta_sync<NT>();
+        for (int j = tid; j < n_old; j += NT) {
+            const float4 v = hpos[j];
+            if (v.x < 0.5f * DEAD_X) atomicAdd(&cell_fill[cell_index(H, v.x, v.y, v.z)], 1);
+        }
+        cta_sync<NT>();
+        if (warp == 0) {
+            int run = 0;
+            for (int base = 0; base < nc; base += 32) {
+                const int c = base + lane;
+                const int v = c < nc ? cell_fill[c] : 0;
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                if (c < nc) { cell_start[c] = run + inc - v; cell_fill[c] = 0; }
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) cell_start[nc] = run;
+        }
+        cta_sync<NT>();
+        for (int j = tid; j < n_old; j += NT) {
+            const float4 v = hpos[j];
+            if (v.x < 0.5f * DEAD_X) {
+                const int c = cell_index(H, v.x, v.y, v.z);
+                const int q = cell_start[c] + atomicAdd(&cell_fill[c], 1);
+                hpos2[q] = make_float4(v.x, v.y, v.z, __int_as_float(j));
+            }
+        }
+        cta_sync<NT>();
+        for (int c = tid; c < nc; c += NT) {          // deterministic order inside each cell: by old slot
+            const int j0 = cell_start[c], j1 = cell_start[c + 1];
+            for (int a = j0 + 1; a < j1; a++) {
+                const float4 v = hpos2[a];
+                const int id = __float_as_int(v.w);
+                int b = a - 1;
+                while (b >= j0 && __float_as_int(hpos2[b].w) > id) { hpos2[b + 1] = hpos2[b]; b--; }
+                hpos2[b + 1] = v;
+            }
+        }
+        cta_sync<NT>();
+        for (int q = tid; q < n_old; q += NT) {
+            if (q < n_alive) {
+                float4 v = hpos2[q];
+                hmap[__float_as_int(v.w)] = q;
+                v.w = __int_as_float(q);
+                hpos[q] = v;
+            } else {
+                hpos[q].x = DEAD_X;
+            }
+        }
+        for (int w = tid; w < cfg.bm_words; w += NT) {
+            const int lo = 32 * w;
+            hole_bm[w] = lo + 32 <= n_alive ? 0xffffffffu : (lo >= n_alive ? 0u : ((1u << (n_alive - lo)) - 1u));
+        }
+        cta_sync<NT>();
+        for (int sl = tid; sl < n_slots; sl += NT) {
+            const uint32_t nn = near[sl];
+            if (nn != NEAR_DEAD) near[sl] = (NearT)hmap[nn];
+        }
+        H.n_h0 = n_alive; H.n_slots = n_alive; n_fill_alive = 0;
+        lists_valid = false;                       // the lists name old slots
+        cta_sync<NT>();
+    };
+    // The KC nearest alive holes of every electron, searched in the grid (after a regrid: all holes).  cr[] / near[] are
+    // NOT touched: the cache stays stale where it is stale; the lists only say what a re-search would find.
+    auto rebuild_lists = [&]() {
+        for (int sl = warp; sl < n_slots; sl += NW) {
+            if (!(cr[sl] < F_INF)) continue;                        // warp-uniform
+            unsigned long long b[KC];
+            warp_nearest_k(H, ex[sl], ey[sl], ez[sl], lane, b);
+            if (lane < KC) {
+                unsigned long long mine = b[0];
+#pragma unroll
+                for (int k = 1; k < KC; k++) if (lane == k) mine = b[k];
+                const bool ok = mine != ~0ull;
+                reinterpret_cast<float *>(cand_d + sl)[lane] = ok ? sqrtf(__uint_as_float((uint32_t)(mine >> 32))) : F_INF;
+                cand_j[(size_t)sl * KC + lane] = ok ? (NearT)(uint32_t)mine : (NearT)NEAR_DEAD;
+            }
+        }
+        cta_sync<NT>();
+        lists_valid = true;
     };
 
     for (int sg = 0; sg < rp.seg_count && status == MCL_OK; sg++) {
@@ -696,6 +823,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             has_cb = g > fminf(A1, A2) - cr_far - 30.0f;
         };
         set_T(0.0);
+        // A dose-free leg after fills (irradiation -> read-out): nothing can be added during the leg, so fresh candidate
+        // lists stay exact for all of it and re-targeting is a lookup again instead of a grid search per hit.
+        if (cfg.relist && can_regrid && !lab && !dose_on && ever_filled && !lists_valid && n_e > 0) { regrid(); rebuild_lists(); }
 
         // The step loop exists twice.  FAST: the simulate protocol without a dose, without per-step records and while no
         // hole was ever added -- what BASELINE-sized ensembles run; protocol, dose, trace and fill-mode branches are compiled
@@ -727,6 +857,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 // A thread owns whole CHUNKS of SPC = 4 slots (chunk b = slots 4b.. belongs to thread b % NT): one 16-byte
                 // load feeds the clocks of a chunk and the post-event scan reads its nearest-hole slots with one load.
                 const int n_chunks = (n_slots + SPC - 1) / SPC;
+                const float A_fast = fmaxf(A1, A2);
                 auto pair_loop = [&](auto with_cb, auto one_channel) {
                     constexpr bool CB = decltype(with_cb)::value;
                     constexpr bool ONE = decltype(one_channel)::value;     // both tunnelling channels identical
@@ -750,36 +881,39 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         for (int q = 0; q < NCH; q++) philox4x32_10(w[q][0], w[q][1], w[q][2], w[q][3], K);
 #pragma unroll
                         for (int q = 0; q < NCH; q++) {
-                            uint32_t ch2 = 0u;                             // bit k: slot k of the chunk uses channel 2
-                            if (!ONE) {
-                                uint32_t tie = 0u;
-#pragma unroll
-                                for (int k = 0; k < 4; k++) {
-                                    const uint32_t sel = w[q][k] & 0x1ffu;
-                                    ch2 |= (sel < sel_T9) ? (1u << k) : 0u;
-                                    tie |= (sel == sel_T9) ? (1u << k) : 0u;
-                                }
-                                if (tie && sel_frac) {                     // 2^-9 per slot, and only when Retrap * 512 has a remainder
-                                    const uint4 tw = philox_tie_words((uint32_t)(b0 + q * NT), (uint32_t)rec_i, rid_lo, rid_hi | (DOM_SEL << 28), K.k[0], K.k[1]);
-                                    const uint32_t t4[4] = {tw.x, tw.y, tw.z, tw.w};
-#pragma unroll
-                                    for (int k = 0; k < 4; k++) ch2 |= (((tie >> k) & 1u) && t4[k] < sel_frac) ? (1u << k) : 0u;
-                                }
-                            }
 #pragma unroll
                             for (int k = 0; k < 4; k++) {
                                 const float le = lg2_fast(-lg2_fast(u01(w[q][k])));
-                                const float Ak = (!ONE && ((ch2 >> k) & 1u)) ? A2 : A1;
+                                float Ak = A1;
+                                bool tie = false;
+                                if (!ONE) {
+                                    const uint32_t sel = w[q][k] & 0x1ffu;
+                                    Ak = sel < sel_T9 ? A2 : A1;
+                                    tie = sel == sel_tie;                  // sel_tie is out of range when Retrap * 512 has no remainder
+                                }
                                 float l;
                                 if (CB) {
                                     // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
-                                    const float a = Ak - cs[q][k];
-                                    const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
-                                    l = (le - kk) + (cs[q][k] - cs[q][k]);
+                                    auto clock_cb = [&](float A_) {
+                                        const float a = A_ - cs[q][k];
+                                        const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
+                                        return (le - kk) + (cs[q][k] - cs[q][k]);
+                                    };
+                                    l = clock_cb(Ak);
+                                    if (!ONE && __builtin_expect(tie, 0)) {
+                                        if (philox_tie_is_ch2((uint32_t)(b0 + q * NT), (uint32_t)rec_i, rid_lo, rid_hi | (DOM_SEL << 28), K.k[0], K.k[1], k, sel_frac))
+                                            l = clock_cb(A2);
+                                    }
                                 } else if (ONE) {
                                     l = le + cs[q][k];                     // the uniform prefactor A1 is subtracted after the loop
                                 } else {
-                                    l = (le + cs[q][k]) - Ak;
+                                    const float base = le + cs[q][k];
+                                    l = base - Ak;
+                                    // a tied selector only needs settling if the electron could win with the faster channel
+                                    if (__builtin_expect(tie && base - A_fast < best, 0)) {
+                                        if (philox_tie_is_ch2((uint32_t)(b0 + q * NT), (uint32_t)rec_i, rid_lo, rid_hi | (DOM_SEL << 28), K.k[0], K.k[1], k, sel_frac))
+                                            l = base - A2;
+                                    }
                                 }
                                 if (l < best) { best = l; bslot = 4 * (b0 + q * NT) + k; }
                             }
@@ -798,7 +932,10 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     // ties on the FP32 clock go to the SMALLEST SLOT (a thread keeps its lowest slot already: ascending
                     // chunks, strict <), so the winner does not depend on which thread owns which slot -- i.e. on NT
                     float wv = warp_min_f32(best);
-                    int ws_ = (int)warp_min_u32(best == wv ? (uint32_t)bslot : 0xffffffffu);     // -1 when the warp has no clock
+                    const unsigned m = __ballot_sync(0xffffffffu, best == wv);
+                    int ws_;
+                    if (m & (m - 1u)) ws_ = (int)warp_min_u32(best == wv ? (uint32_t)bslot : 0xffffffffu);   // tie (2^-18 per step), or no clock at all: -1
+                    else ws_ = __shfl_sync(0xffffffffu, bslot, m ? (__ffs(m) - 1) : 0);
                     __syncwarp();
                     if (lane == 0) red_row[par][warp] = make_int4(__float_as_int(wv), ws_, ws_ >= 0 ? (int)near[ws_] : -1, 0);
                 }
@@ -826,31 +963,32 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     const float v = __int_as_float(row.x);
                     const int s = row.y, hh = row.z;
                     vmin = warp_min_f32(v);
-                    if (sizeof(NearT) == 2) {
-                        // slot < 2^15 and hole < 2^16: one packed minimum gives the smallest tied slot and its hole
-                        const uint32_t key = (v == vmin && s >= 0) ? (((uint32_t)s << 16) | ((uint32_t)hh & 0xffffu)) : 0xffffffffu;
-                        const uint32_t k = warp_min_u32(key);
-                        smin = k == 0xffffffffu ? -1 : (int)(k >> 16);
-                        hmin = k == 0xffffffffu ? -1 : (int)(k & 0xffffu);
-                    } else {
-                        smin = (int)warp_min_u32(v == vmin ? (uint32_t)s : 0xffffffffu);
-                        const unsigned m = __ballot_sync(0xffffffffu, v == vmin && s == smin);
-                        hmin = __shfl_sync(0xffffffffu, hh, m ? (__ffs(m) - 1) : 0);
+                    unsigned m = __ballot_sync(0xffffffffu, v == vmin);
+                    if (m & (m - 1u)) {             // tied rows (or no clock anywhere): the smallest slot wins, whatever warp holds it
+                        const int s_low = (int)warp_min_u32(v == vmin ? (uint32_t)s : 0xffffffffu);
+                        m = __ballot_sync(0xffffffffu, v == vmin && s == s_low);
                     }
+                    const int src = m ? (__ffs(m) - 1) : 0;
+                    smin = __shfl_sync(0xffffffffu, s, src);
+                    hmin = __shfl_sync(0xffffffffu, hh, src);
                 }
                 // ---------------- filling clock (tl_trap_lab.py:53-60) and dt (simulate.py:58-60)
-                // Without a dose the clock is exponential(1e20 s) >= -ln(1 - 2^-24) * 1e20 = 5.96e12 s: it can only matter (the
-                // reference's spurious fill) when nothing else happens before 5e12 s -- otherwise it is not evaluated.
+                // Without a dose the clock is exponential(1e20 s).  The smallest draw of the 24-bit uniform is -lg2(1 - 2^-24) =
+                // 8.6e-8, but `lg2.approx` is only good to ~2^-23 ABSOLUTE there (measured: 1.2e-8 comes out,
+                // tests/test_gpu_bench_shapes.py), so the clock's draw is clamped at 5e-8: dt_fill >= 5e-8 ln2 1e20 = 3.47e12 s.
+                // It can only matter (the reference's spurious fill) when nothing else happens before 3e12 s --
+                // otherwise it is not evaluated.
                 const float dt_rec0 = n_e > 0 ? ex2_fast(vmin) * LN2F : F_INF;
                 float dt_fill = F_INF;
-                if (FAST && !(fminf(dt_rec0, dt_cap) < 5.0e12f)) {
+                if (FAST && !(fminf(dt_rec0, dt_cap) < 3.0e12f)) {
                     // the filling clock could matter (spurious fill): the general loop repeats this step
                     cta_sync<NT>();
                     return false;
                 }
-                if (dose_on || !((lab ? dt_rec0 : fminf(dt_rec0, dt_cap)) < 5.0e12f)) {       // (the lab loops have no step cap)
+                if (dose_on || !((lab ? dt_rec0 : fminf(dt_rec0, dt_cap)) < 3.0e12f)) {       // (the lab loops have no step cap)
                     float lam = (n_e == rp.N_e || !dose_on) ? 1e-20f : dose_over_D0 * (float)(rp.N_e - n_e);
-                    dt_fill = lam > 0.0f ? __fdividef(-lg2_fast(u01(stepdraw[(rec_i >> 5) & 1][rec_i & 31][0])) * LN2F, lam) : 1e20f;
+                    const float e2 = fmaxf(-lg2_fast(u01(stepdraw[(rec_i >> 5) & 1][rec_i & 31][0])), 5.0e-8f);
+                    dt_fill = lam > 0.0f ? __fdividef(e2 * LN2F, lam) : 1e20f;
                 }
                 const float dt_rec = n_e > 0 ? dt_rec0 : dt_fill;
                 float dt; bool is_fill, is_rec;
@@ -915,7 +1053,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                             if (b >= 0 && b < p.hist.n_bins) atomicAdd(&p.hist_events[(size_t)hrow * p.hist.n_bins + b], 1ull);
                         }
                     }
-                    if (h >= n_h0) n_fill_alive--;
+                    if (h >= H.n_h0) n_fill_alive--;
                     // Which of MY other electrons were cached on h (or h2)?  A thread owns the pairs it sweeps
                     // (q = tid, tid + NT, ...), and only the owner ever touches cr[] / near[] of a pair outside
                     // barrier-protected phases -- so re-targeting needs no CTA barrier at all.
@@ -926,8 +1064,8 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     int redo = -1;                      // a slot of mine that needs the warp-cooperative search
                     auto retarget = [&](int sl) {
                         bool fixed = false;
-                        if (!ever_filled) {
-                            // no hole was ever added: the new nearest is the first remembered candidate that is
+                        if (lists_valid) {
+                            // no hole was added since the lists were built: the new nearest is the first remembered candidate that is
                             // still alive (and is not the hole dying now, whose bitmap bit may not be visible yet)
                             // distances and slots of the list are fetched together: ONE round trip to L2 / HBM
                             const float4 d4 = cand_d[sl];
@@ -945,7 +1083,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                                 const uint32_t j = cj[c];
                                 if (!fixed && j != NEAR_DEAD && j != (uint32_t)h && ((hole_bm[j >> 5] >> (j & 31)) & 1u)) {
                                     cr[sl] = dk[c]; near[sl] = (NearT)j; fixed = true;
-                                    if (share_bm) mark_target(j, sl);
+                                    if (share_bm && !ever_filled) mark_target(j, sl);
                                 }
                             }
                         }
@@ -1051,7 +1189,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                             for (int k = 0; k < KC; k++) cj[k] = (NearT)NEAR_DEAD;
                             if (alive) {
                                 x = ex[s]; y = ey[s]; z = ez[s];
-                                if (!ever_filled) {
+                                if (lists_valid) {
                                     cd = cand_d[s];
 #pragma unroll
                                     for (int k = 0; k < KC; k++) cj[k] = cand_j[(size_t)s * KC + k];
@@ -1068,7 +1206,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                             cta_sync<NT>();                       // all reads of this tile done
                             if (alive) {
                                 cr[dst] = c; near[dst] = nn; ex[dst] = x; ey[dst] = y; ez[dst] = z;
-                                if (!ever_filled) {
+                                if (lists_valid) {
                                     cand_d[dst] = cd;
 #pragma unroll
                                     for (int k = 0; k < KC; k++) cand_j[(size_t)dst * KC + k] = cj[k];
@@ -1093,11 +1231,13 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 } else if (is_fill) {
                     // ---------------- Box.add_electron (engine.py:133-152), done by warp 0
                     ever_filled = true;
+                    lists_valid = false;
                     int es = -1;
                     if (n_e == n_slots) es = n_slots;             // no tombstone to reuse
                     const bool append_e = (es >= 0);
                     if (append_e && es >= cfg.cap_slots - 4) { status = MCL_ERR_CAPACITY; break; }
-                    const bool append_h = (n_fill_alive == H.n_slots - n_h0);
+                    bool append_h = (n_fill_alive == H.n_slots - H.n_h0);
+                    if (append_h && can_regrid && H.n_slots - H.n_h0 >= fill_cap) regrid();   // fill region full of alive holes: fold it into the grid
                     if (append_h && H.n_slots >= p.cap_h) { status = MCL_ERR_CAPACITY; break; }
                     if (warp == 0) {
                         if (!append_e) {
@@ -1110,7 +1250,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         int hs = H.n_slots;
                         if (!append_h) {
                             hs = -1;
-                            for (int base = n_h0; base < H.n_slots && hs < 0; base += 32) {
+                            for (int base = H.n_h0; base < H.n_slots && hs < 0; base += 32) {
                                 int j = base + lane;
                                 unsigned m = __ballot_sync(0xffffffffu, j < H.n_slots && !((hole_bm[j >> 5] >> (j & 31)) & 1u));
                                 if (m) hs = base + __ffs(m) - 1;
@@ -1237,12 +1377,16 @@ static int grid_edge_max(int n_h0_max)
     return g < 1 ? 1 : g;
 }
 
-struct PhiloxPlan { int nt; int cap_slots; int g_max; int cap_cells; int bm_words; int share_bm; int ref_words; size_t smem; size_t off_holes; size_t off_cand; size_t stride; bool near16; };
+struct PhiloxPlan {
+    int nt; int cap_slots; int g_max; int cap_cells; int bm_words; int share_bm; int ref_words; size_t smem; size_t off_holes; size_t off_cand;
+    size_t off_hpos2, off_hmap; size_t stride; bool near16;
+    bool slab_smem; int sm_hpos, sm_exyz, sm_cstart, sm_cfill;
+};
 
 static int g_nt_override = 0;
 void philox_set_block_threads(int nt) { g_nt_override = nt; }
 
-static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override, int n_replicas = 1 << 30)
+static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override, int n_replicas = 1 << 30, bool with_regrid = true)
 {
     PhiloxPlan pl;
     pl.cap_slots = (int)align_up((size_t)cap_e + 2, 64);
@@ -1255,7 +1399,9 @@ static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override, int n_replica
     pl.off_holes = align_up(sizeof(float) * 3 * (size_t)cap_e, 16);
     size_t b = pl.off_holes + 16 * (size_t)cap_h + sizeof(int) * (2 * (size_t)pl.cap_cells + (size_t)cap_e);
     pl.off_cand = align_up(b, 16);
-    pl.stride = align_up(pl.off_cand + (size_t)cap_e * (16 + 4 * (pl.near16 ? 2 : 4)), 256);
+    pl.off_hpos2 = align_up(pl.off_cand + (size_t)cap_e * (16 + 4 * (pl.near16 ? 2 : 4)), 16);
+    pl.off_hmap = pl.off_hpos2 + (with_regrid ? 16 * (size_t)cap_h : 0);
+    pl.stride = align_up(pl.off_hmap + (with_regrid ? 4 * (size_t)cap_h : 0), 256);
     // CTA width: throughput optimum measured on B200 (2000 electrons: 64 threads, 10^4: 256).  Results do not
     // depend on it.  With fewer replicas than SMs the launch is latency-bound: widen the CTAs instead.
     int nt;
@@ -1275,29 +1421,49 @@ static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override, int n_replica
     pl.ref_words = (cap_h + 7) / 8;
     if (nt < 256) pl.share_bm = 0;
     if (pl.share_bm) pl.smem += 4 * ((size_t)pl.bm_words + (size_t)pl.ref_words);
+    // Small boxes (one warp per replica): hole table, cell tables and electron coordinates in shared memory when at least
+    // four such CTAs fit an SM.  MCL_PHILOX_SMEM_SLAB=0 keeps them in the HBM slab (same results; test knob).
+    pl.slab_smem = false; pl.sm_hpos = pl.sm_exyz = pl.sm_cstart = pl.sm_cfill = 0;
+    if (nt == 32) {
+        size_t o = align_up(pl.smem, 16);
+        const size_t o_hpos = o; o += 16 * (size_t)cap_h;
+        const size_t o_exyz = o; o += 12 * (size_t)cap_e;
+        const size_t o_cstart = o; o += 4 * (size_t)pl.cap_cells;
+        const size_t o_cfill = o; o += 4 * (size_t)pl.cap_cells;
+        bool want = o <= 56 * 1024;
+        if (const char *env = getenv("MCL_PHILOX_SMEM_SLAB")) want = want && atoi(env) != 0;
+        if (want) {
+            pl.slab_smem = true; pl.smem = o;
+            pl.sm_hpos = (int)(o_hpos / 4); pl.sm_exyz = (int)(o_exyz / 4); pl.sm_cstart = (int)(o_cstart / 4); pl.sm_cfill = (int)(o_cfill / 4);
+        }
+    }
     return pl;
 }
 
-size_t philox_ws_stride(int cap_e, int cap_h)
+size_t philox_ws_stride(int cap_e, int cap_h, bool with_regrid)
 {
-    return make_plan(cap_e, cap_h, 0).stride;
+    return make_plan(cap_e, cap_h, 0, 1 << 30, with_regrid).stride;
 }
 
-template <int NT, int MINB, typename NearT, int PPC>
+template <int NT, int MINB, typename NearT, int PPC, bool SLAB_SMEM = false>
 static cudaError_t launch_one(const LaunchParams &p, const RoundKeys &K, const Cfg &cfg, size_t smem, cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(philox_kernel<NT, MINB, NearT, PPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(philox_kernel<NT, MINB, NearT, PPC, SLAB_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    philox_kernel<NT, MINB, NearT, PPC><<<p.n_replicas, NT, smem, stream>>>(p, K, cfg);
+    philox_kernel<NT, MINB, NearT, PPC, SLAB_SMEM><<<p.n_replicas, NT, smem, stream>>>(p, K, cfg);
     return cudaGetLastError();
 }
 
 cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_slots*/)
 {
-    PhiloxPlan pl = make_plan(p.cap_e, p.cap_h, g_nt_override, p.n_replicas);
+    PhiloxPlan pl = make_plan(p.cap_e, p.cap_h, g_nt_override, p.n_replicas, p.with_regrid != 0);
     int fast = 1;
     if (const char *env = getenv("MCL_PHILOX_FAST")) fast = atoi(env) != 0;        // knob: 0 = general step loop only
-    Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.share_bm, pl.ref_words, pl.off_holes, pl.off_cand, fast};
+    int fill_extra = kFillExtra, relist = 1;
+    if (const char *env = getenv("MCL_PHILOX_FILL_EXTRA")) { int v = atoi(env); fill_extra = v > kFillExtra ? kFillExtra : v; }   // test knob: regrid early (may be negative)
+    if (const char *env = getenv("MCL_PHILOX_RELIST")) relist = atoi(env) != 0;    // knob: 0 = read-out legs after fills keep searching the grid
+    Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.share_bm, pl.ref_words, pl.off_holes, pl.off_cand, fast,
+            pl.off_hpos2, pl.off_hmap, fill_extra, p.with_regrid != 0, relist, pl.sm_hpos, pl.sm_exyz, pl.sm_cstart, pl.sm_cfill};
     RoundKeys K;
     uint64_t s = mix64(p.seed);
     uint32_t k0 = (uint32_t)s, k1 = (uint32_t)(s >> 32);
@@ -1307,6 +1473,9 @@ cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_
     case NT_:                                                                                      \
         return pl.near16 ? launch_one<NT_, MINB_, uint16_t, PPC_>(p, K, cfg, pl.smem, stream)      \
                          : launch_one<NT_, MINB_, uint32_t, PPC_>(p, K, cfg, pl.smem, stream)
+    if (pl.slab_smem)       // (implies nt == 32) few CTAs per SM: no register cap worth the name
+        return pl.near16 ? launch_one<32, 12, uint16_t, 2, true>(p, K, cfg, pl.smem, stream)
+                         : launch_one<32, 12, uint32_t, 2, true>(p, K, cfg, pl.smem, stream);
     switch (pl.nt) {
         MCL_CASE(32, 32, 2);
         MCL_CASE(64, 16, 2);

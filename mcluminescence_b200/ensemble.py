@@ -114,3 +114,44 @@ def run_ensemble(workload: Dict[str, Any], *, seed: int, rank: int = 0, world: i
             n_replicas=n_global, esteps=int(c[0]), steps=int(c[1]), errors=int(c[2]), final_n_e_sum=int(c[3]))
 
     return finish, T
+
+
+def run_population(P: np.ndarray, cfg, exp: str, *, seed: int, rank: int = 0, world: int = 1, group=None,
+                   shard: bool = True, candidate_id0: int = 0):
+    """Optimizer population across GPUs (``src/class/optimizer.py:104-111`` maps ``objective`` over a process pool):
+    every rank evaluates its block of candidates with one ``mcl_objective`` call, then ONE all-gather returns the
+    objective values to every rank (plus an all-reduce of two counters).  Candidate ``c`` uses the Philox streams of
+    global id ``candidate_id0 + c`` whatever the number of ranks.
+
+    ``shard=True``: ``P[10, S]`` is the global population, this rank takes its block.  ``shard=False``: ``P`` is this
+    rank's own population (weak scaling), global ids offset by rank.
+    Returns ``(mse_global[S_total], electron_steps_global, kernel_ms_this_rank)``.
+    """
+    from . import _native, optimizer
+    torch = engine._torch()
+    S = int(P.shape[1])
+    if shard:
+        lo, hi = shard_bounds(S, world, rank)
+        mine, id0, S_total = P[:, lo:hi], candidate_id0 + lo, S
+    else:
+        mine, id0, S_total = P, candidate_id0 + rank * S, S * world
+    if mine.shape[1] > 0:
+        mse, es = optimizer.objective_batched(np.ascontiguousarray(mine), cfg, exp, seed=seed, candidate_id0=id0,
+                                              return_esteps=True)
+        kernel_ms = float(_native.load().mcl_objective_last_kernel_ms())
+    else:
+        mse, es, kernel_ms = np.zeros(0), 0, 0.0
+    if world == 1:
+        return mse, es, kernel_ms
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    counts = [shard_bounds(S, world, r)[1] - shard_bounds(S, world, r)[0] for r in range(world)] if shard else [S] * world
+    pad = max(counts)
+    buf = torch.zeros(pad, dtype=torch.float64, device=dev)
+    buf[:mse.size] = torch.as_tensor(mse, dtype=torch.float64)
+    gathered = [torch.zeros(pad, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, buf, group=group)
+    tot = torch.tensor([es], dtype=torch.int64, device=dev)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    out = np.concatenate([g[:n].cpu().numpy() for g, n in zip(gathered, counts)])
+    return out, int(tot.item()), kernel_ms

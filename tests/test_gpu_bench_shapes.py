@@ -258,13 +258,20 @@ def test_small_waiting_time_tail_of_the_sfu_draw(gpu):
     exact = -np.log2(u)
     assert np.all(np.isfinite(a)) and np.all(a > 0), "a draw came out zero, negative or non-finite"
     assert np.all(np.isfinite(b))
-    rel = a.astype(np.float64) / exact - 1.0
+    err = a.astype(np.float64) - exact
+    rel = err / exact
+    near1 = u > 0.5
     tail = exact < 1e-5 / np.log(2.0)
-    print(f"SFU draw: tail (E<1e-5) rel. error mean {rel[tail].mean():+.2e} max {np.abs(rel[tail]).max():.2e}; "
-          f"bulk max {np.abs(rel[~tail]).max():.2e}; smallest draw {a.min():.3e} (exact {exact.min():.3e})")
-    assert np.abs(rel[tail]).max() < 0.08 and abs(rel[tail].mean()) < 2e-3
-    assert np.abs(rel[~tail]).max() < 2e-3
+    print(f"SFU draw: abs. error for u in (0.5, 1): mean {err[near1].mean():+.2e} max {np.abs(err[near1]).max():.2e} (2^-22 = {2.0**-22:.2e}); "
+          f"tail (E<1e-5) rel. error mean {rel[tail].mean():+.2e}; smallest draw {a.min():.3e} (exact {exact.min():.3e})")
+    # what PTX promises near u -> 1 is an ABSOLUTE error of 2^-22; measured on B200: a near-constant -7e-8, i.e. draws of
+    # size E are short by 7e-8 / E -- 5e-4 of the minimum of 10^4 equal clocks, the worst case the path has
+    # (test_cb_dominated_large_box_decays_exponentially bounds its effect on the decay rate)
+    assert np.abs(err[near1]).max() < 2.0 ** -22
+    assert np.abs(err[near1 & (exact > 1e-4)] / exact[near1 & (exact > 1e-4)]).max() < 1.5e-3
+    assert np.abs(rel[~near1]).max() < 1e-5
     # outer logarithm (what enters the argmin): absolute error in log2 units
     assert np.abs(b.astype(np.float64) - np.log2(a.astype(np.float64))).max() < 2e-5
-    # dose-free filling clock: exponential(1e20 s) >= smallest draw * ln2 * 1e20 must stay above the 5e12 s threshold
-    assert a.min() * np.log(2.0) * 1e20 > 5.0e12
+    # dose-free filling clock exponential(1e20 s): the kernel clamps its draw at 5e-8 (below the exact minimum 8.6e-8,
+    # above the SFU's worst) and skips the clock while something else happens before 3e12 s
+    assert exact.min() > 5.0e-8 and 5.0e-8 * np.log(2.0) * 1e20 > 3.0e12

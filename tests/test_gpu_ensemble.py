@@ -314,3 +314,30 @@ def test_specialised_step_loop_changes_no_result(gpu):
                 assert np.array_equal(fast.hist_occ, other.hist_occ), wl["name"]
     # the last job ends with a handful of electrons whose next clock is beyond 5e12 s: the hand-over step
     assert 0 < int(fast.final_n_e.max()) < int(jobs[-1]["replicas"]["n_e0"][0]) // 2
+
+
+def test_shared_memory_slab_changes_no_result(gpu, capsys):
+    """Small boxes (the Optimizer path) keep their hole table, cell tables and electron coordinates in shared memory;
+    `MCL_PHILOX_SMEM_SLAB=0` keeps them in the HBM slab.  Same algorithm: every objective value and electron-step
+    count must be identical -- TL rows with fills and regrids, isothermal experiments with observation times."""
+    import os
+    from mcluminescence_b200 import optimizer
+    from mcluminescence_b200.config import compose
+    from mcluminescence_b200.workloads import c4_candidates
+    cfg = compose(overrides=helpers.LAB_OVERRIDES)
+    P = c4_candidates(64, seed=9)
+    for exp in ("tl_clbr", "iso"):
+        for extra in (None, "-92"):
+            if extra is not None:
+                os.environ["MCL_PHILOX_FILL_EXTRA"] = extra
+            try:
+                a, ea = optimizer.objective_batched(P, cfg, exp, seed=31, return_esteps=True)
+                os.environ["MCL_PHILOX_SMEM_SLAB"] = "0"
+                try:
+                    b, eb = optimizer.objective_batched(P, cfg, exp, seed=31, return_esteps=True)
+                finally:
+                    del os.environ["MCL_PHILOX_SMEM_SLAB"]
+            finally:
+                os.environ.pop("MCL_PHILOX_FILL_EXTRA", None)
+            assert np.array_equal(a, b) and ea == eb, (exp, extra)
+    capsys.readouterr()
