@@ -107,9 +107,11 @@ def load():
         L.mcl_objective.restype = C.c_int
         L.mcl_objective.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Lab), C.c_uint64, C.c_uint64,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
-    L.mcl_objective_last_kernel_ms.restype = C.c_float
-    L.mcl_debug_exp_draws.restype = C.c_int
-    L.mcl_debug_exp_draws.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    if hasattr(L, "mcl_objective_last_kernel_ms"):       # (older A/B builds named by MCL_B200_LIB may lack the newer hooks)
+        L.mcl_objective_last_kernel_ms.restype = C.c_float
+    if hasattr(L, "mcl_debug_exp_draws"):
+        L.mcl_debug_exp_draws.restype = C.c_int
+        L.mcl_debug_exp_draws.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     if L.mcl_abi_version() != ABI_VERSION:
         raise NativeError(f"libmcl_b200.so ABI {L.mcl_abi_version()} != expected {ABI_VERSION}")
     _lib = L

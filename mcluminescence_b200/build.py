@@ -23,7 +23,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "--extended-lambda", "-Xcompiler", "
           "-I", INCLUDE, "-I", CSRC]
 # per-file extras: the replay kernel must never fuse a multiply into an add (NumPy does not)
 EXTRA = {"mcl_replay.cu": ["-fmad=false"]}
-SOURCES = ["mcl_abi.cu", "mcl_replay.cu", "mcl_philox.cu", "mcl_peaks.cu", "mcl_objective.cu"]
+SOURCES = ["mcl_abi.cu", "mcl_replay.cu", "mcl_philox.cu", "mcl_smallbox.cu", "mcl_peaks.cu", "mcl_objective.cu"]
 
 
 def nvcc() -> str:

@@ -2,7 +2,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
+#include <algorithm>
 #include <vector>
 #include "mcl_common.cuh"
 
@@ -19,11 +21,31 @@ void set_error(const char *fmt, ...)
 }
 
 struct Layout {
-    size_t off_rep, off_seg, off_obs, off_grp, off_slabs, total;
+    size_t off_rep, off_seg, off_obs, off_grp, off_order, off_slabs, total;
     size_t stride;
     int cap_e, cap_h;
     bool any_dose;
+    // Which kernel runs which replica, decided per replica from its own fields: `small` -> one warp per replica
+    // (mcl_smallbox.cu, the Optimizer path), `big` -> one CTA per replica (mcl_philox.cu / mcl_replay.cu).  Both lists are
+    // ordered longest-expected-work first: blocks are dispatched in index order, so the hardware scheduler is the work
+    // queue and the long replicas do not end up in the tail of the launch.
+    std::vector<int32_t> small, big;
+    int small_hcap;
 };
+
+// expected work of a replica, up to a constant: what the launch order sorts by
+static double work_estimate(const mcl_run_args *a, const mcl_replica &rp)
+{
+    const double n = (double)std::max(rp.N_e, rp.n_e0);
+    if (rp.protocol == MCL_PROTO_ISO_LAB)
+        return n * (rp.obs_count > 0 && a->obs_time ? a->obs_time[rp.obs_begin + rp.obs_count - 1] : 0.0);
+    double w = 0.0;
+    for (int s = 0; s < rp.seg_count; s++) {
+        const mcl_segment &sg = a->segments[rp.seg_begin + s];
+        w += std::min(sg.duration, 1e9) * (sg.dose_rate != 0.0 ? 2.0 : 1.0);
+    }
+    return n * w;
+}
 
 static int plan_layout(const mcl_run_args *a, Layout *L)
 {
@@ -35,6 +57,9 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
     if (a->hist && (a->hist->n_bins <= 0 || a->hist->n_groups <= 0 || !(a->hist->hi > a->hist->lo))) { set_error("mcl_run: bad histogram spec"); return MCL_ERR_ARG; }
     int ne_max = 0, nh_max = 0, seg_max = 1;
     bool any_dose = false;
+    L->small.clear(); L->big.clear(); L->small_hcap = 0;
+    bool small_ok = a->mode == MCL_MODE_PHILOX && !a->hist && !a->kind && !a->e_idx && !a->h_idx;
+    if (const char *env = getenv("MCL_SMALLBOX")) small_ok = small_ok && atoi(env) != 0;       // test knob: 0 = block kernel for every replica
     for (int r = 0; r < a->n_replicas; r++) {
         const mcl_replica &rp = a->replicas[r];
         if (rp.N_e < 0 || rp.n_e0 < 0 || rp.n_h0 < 0) { set_error("replica %d: negative sizes", r); return MCL_ERR_ARG; }
@@ -46,6 +71,12 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
         if (rp.protocol != MCL_PROTO_SIMULATE && rp.seg_count != 1) { set_error("replica %d: lab protocols take exactly one segment", r); return MCL_ERR_ARG; }
         if (rp.obs_count < 0 || rp.obs_begin < 0 || rp.obs_begin + rp.obs_count > a->n_obs) { set_error("replica %d: observation range outside table", r); return MCL_ERR_ARG; }
         if (rp.obs_count > 0 && !a->obs_time) { set_error("replica %d: obs_time missing", r); return MCL_ERR_ARG; }
+        if (small_ok && smallbox_eligible(rp)) {          // sized separately: these replicas never see a slab
+            L->small.push_back(r);
+            L->small_hcap = std::max(L->small_hcap, smallbox_hole_capacity(rp));
+            continue;
+        }
+        L->big.push_back(r);
         ne_max = std::max(ne_max, std::max(rp.N_e, rp.n_e0));
         nh_max = std::max(nh_max, rp.n_h0);
         seg_max = std::max(seg_max, rp.seg_count);
@@ -69,7 +100,15 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
     L->off_seg = o; o = align_up(o + sizeof(mcl_segment) * (size_t)a->n_segments, 256);
     L->off_obs = o; o = align_up(o + sizeof(double) * (size_t)std::max(a->n_obs, 1), 256);
     L->off_grp = o; o = align_up(o + sizeof(int32_t) * (size_t)a->n_replicas, 256);
-    L->off_slabs = o; o += L->stride * (size_t)a->n_replicas;
+    L->off_order = o; o = align_up(o + sizeof(int32_t) * (size_t)a->n_replicas, 256);
+    L->off_slabs = o; o += L->stride * L->big.size();
+    if (a->mode == MCL_MODE_PHILOX) {
+        std::vector<double> w((size_t)a->n_replicas);
+        for (int r = 0; r < a->n_replicas; r++) w[r] = work_estimate(a, a->replicas[r]);
+        auto by_work = [&](int32_t x, int32_t y) { return w[x] > w[y]; };
+        std::stable_sort(L->small.begin(), L->small.end(), by_work);
+        std::stable_sort(L->big.begin(), L->big.end(), by_work);
+    }
     L->total = o;
     return MCL_OK;
 }
@@ -119,8 +158,22 @@ static int run_device(const mcl_run_args *a, cudaEvent_t ev0 = nullptr, cudaEven
         p.hist_occ_sq = (unsigned long long *)a->hist_occ_sq;
     }
     p.ws = ws + L.off_slabs; p.ws_stride = L.stride; p.cap_e = L.cap_e; p.cap_h = L.cap_h; p.with_regrid = L.any_dose ? 1 : 0;
+    p.order = nullptr; p.n_launch = a->n_replicas;
+    int32_t *order_dev = (int32_t *)(ws + L.off_order);
+    if (a->mode == MCL_MODE_PHILOX) {
+        // [small list | big list] in one upload (pageable host memory: the copy is staged before the call returns)
+        std::vector<int32_t> both(L.small);
+        both.insert(both.end(), L.big.begin(), L.big.end());
+        CUDA_TRY(cudaMemcpyAsync(order_dev, both.data(), sizeof(int32_t) * both.size(), cudaMemcpyHostToDevice, st));
+        p.order = order_dev + L.small.size(); p.n_launch = (int32_t)L.big.size();
+    }
     if (ev0) cudaEventRecord(ev0, st);
-    cudaError_t e = a->mode == MCL_MODE_REPLAY ? launch_replay(p, st) : launch_philox(p, st, 0);
+    cudaError_t e = cudaSuccess;
+    if (a->mode == MCL_MODE_REPLAY) e = launch_replay(p, st);
+    else {
+        if (!L.small.empty()) e = launch_smallbox(p, order_dev, (int)L.small.size(), L.small_hcap, st);
+        if (e == cudaSuccess && !L.big.empty()) e = launch_philox(p, st, 0);
+    }
     if (ev1) cudaEventRecord(ev1, st);
     if (e != cudaSuccess) { set_error("kernel launch: %s", cudaGetErrorString(e)); return MCL_ERR_CUDA; }
     return MCL_OK;

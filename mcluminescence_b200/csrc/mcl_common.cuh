@@ -33,6 +33,9 @@ struct LaunchParams {
     size_t ws_stride;
     int32_t cap_e, cap_h;        // per-replica element capacities inside the scratch
     int32_t with_regrid;         // the slabs carry the regrid scratch (some replica of the launch has a dosed leg)
+    // which replicas this launch runs: block b runs replica order[b] (nullptr: b) and owns slab b; n_launch blocks
+    const int32_t *order;
+    int32_t n_launch;
 };
 
 // Fill-region slots beyond N_e: a fill that finds N_e + kFillExtra of them in use folds them into the cell grid first, so a
@@ -48,6 +51,11 @@ cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int max_sl
 size_t replay_ws_stride(int cap_e, int cap_h);
 size_t philox_ws_stride(int cap_e, int cap_h, bool with_regrid);
 int philox_max_slots();       // largest per-replica electron capacity the block kernel supports
+// one-warp-per-replica kernel of the Optimizer path (mcl_smallbox.cu)
+constexpr int kSmallboxMaxHoles = 4096;
+static inline int smallbox_hole_capacity(const mcl_replica &rp) { return rp.n_h0 + rp.N_e + 8; }   // slots are reused lowest-first
+bool smallbox_eligible(const mcl_replica &rp);
+cudaError_t launch_smallbox(const LaunchParams &p, const int *order_dev, int count, int hcap, cudaStream_t stream);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

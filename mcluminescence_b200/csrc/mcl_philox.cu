@@ -36,14 +36,12 @@
 #include <type_traits>
 #include <cstdlib>
 #include "mcl_common.cuh"
+#include "mcl_rng.cuh"
 
 namespace mcl {
 
 namespace {
 
-constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
-constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
-constexpr uint32_t DOM_SCALAR = 1u, DOM_SEED_E = 2u, DOM_SEED_H = 3u, DOM_STEP1 = 4u, DOM_SEL = 5u;
 #ifndef MCL_SCAN_UNROLL
 #define MCL_SCAN_UNROLL 4
 #endif
@@ -61,7 +59,6 @@ constexpr float DEAD_X = 1e30f;
 constexpr float LN2F = 0.69314718055994530942f;
 constexpr double L2E = 1.4426950408889634074;
 
-struct RoundKeys { uint32_t k[20]; };
 #ifdef MCL_PROFILE_SKEW
 // Profiling build only (scripts/build_variant.sh skew -DMCL_PROFILE_SKEW; scripts/skew_probe.py): cycles per warp index
 // spent in the sweep / waiting at the step barrier / between the barrier and the next sweep, and the step count.
@@ -87,18 +84,6 @@ struct Cfg {
     int sm_hpos, sm_exyz, sm_cstart, sm_cfill;
 };
 
-__device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
-                                              const RoundKeys &K)
-{
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        unsigned long long p0 = (unsigned long long)PHILOX_M0 * c0;
-        unsigned long long p1 = (unsigned long long)PHILOX_M1 * c2;
-        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k[2 * r];
-        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k[2 * r + 1];
-        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
-    }
-}
 
 // Rare path of the channel selector (a 9-bit tie, probability 2^-9 per electron-step): the four words that settle the
 // ties of one chunk.  Out of line, with the round keys rebuilt from the two key words, so that the sweep carries
@@ -119,22 +104,6 @@ __device__ __noinline__ bool philox_tie_is_ch2(uint32_t c0, uint32_t c1, uint32_
     return w < sel_frac;
 }
 
-__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float warp_min_f32(float v)
-{
-    float r;
-    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-    return r;
-}
-__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v)
-{
-    uint32_t r;
-    asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
-    return r;
-}
-// u32 -> uniform on [2^-24, 1 - 2^-24] (exact): one LEA.HI + one FADD, no conversion instruction
-__device__ __forceinline__ float u01(uint32_t r) { return __uint_as_float((r >> 9) | 0x3f800000u) - 0.99999994f; }
 
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 {
@@ -416,14 +385,17 @@ __device__ __noinline__ void seed_candidate_lists_call(const Holes &H, const int
 // SLAB_SMEM: the hole table, the cell tables and the electron coordinates of the replica live in shared memory instead of
 // its HBM slab (small boxes -- the Optimizer path: every nearest-hole search is then a handful of shared-memory reads
 // instead of dependent L2 / HBM round trips).  Same algorithm, same results.
-template <int NT, int MINB, typename NearT, int PPC, bool SLAB_SMEM = false>
+// REGRID: the launch has a dosed leg somewhere (mcl_run sized the slabs for it): regrids and candidate-list rebuilds are
+// compiled in.  Dose-free launches (the BASELINE ensembles) run the instantiation without them, whose hole grid is a
+// set of launch constants again -- fewer live registers in the step loop.
+template <int NT, int MINB, typename NearT, int PPC, bool SLAB_SMEM = false, bool REGRID = true>
 __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, const RoundKeys K, const Cfg cfg)
 {
     constexpr int NW = NT / 32;
     constexpr uint32_t NEAR_DEAD = NearTraits<NearT>::DEAD;
     constexpr int SPC = 2 * PPC;              // slots per chunk: a thread owns whole chunks (chunk b -> thread b % NT)
     static_assert(PPC == 2, "a chunk is four slots: one 16-byte load of cr[], one Philox call when the channels are identical");
-    const int r = blockIdx.x;
+    const int r = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;      // block b runs replica order[b] in slab b
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const mcl_replica rp = p.replicas[r];
     const unsigned long long rid = p.replica_id0 + (unsigned long long)r;
@@ -462,7 +434,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     if (threadIdx.x == 0) s_err = 0;
 
     // ---------------- HBM slab
-    unsigned char *ws = p.ws + (size_t)r * p.ws_stride;
+    unsigned char *ws = p.ws + (size_t)blockIdx.x * p.ws_stride;
     const size_t ce = (size_t)p.cap_e, ch = (size_t)p.cap_h;
     float *ex = reinterpret_cast<float *>(ws), *ey = ex + ce, *ez = ex + 2 * ce;
     float4 *hpos = reinterpret_cast<float4 *>(ws + cfg.off_holes);    // [cap_h] (x, y, z, original index)
@@ -634,6 +606,10 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     const uint32_t sel_T9 = (uint32_t)sel_scaled;
     const uint32_t sel_frac = (uint32_t)fmin((sel_scaled - (double)sel_T9) * 4294967296.0, 4294967295.0);
     const uint32_t sel_tie = sel_frac ? sel_T9 : 0xffffu;           // no remainder: sel9 == T9 is plain channel 1
+    // The sweep first takes a tied selector for the SLOWER channel (a plain compare: sel9 < sel_cmp -> channel 2) and only
+    // settles the ties that could still win the step with the faster one.  Which channel is faster does not depend on T.
+    const bool ch2_fast = rp.E_loc_2 <= rp.E_loc_1;
+    const uint32_t sel_cmp = (sel_frac && !ch2_fast) ? sel_T9 + 1u : sel_T9;
     const float cr_far = bnd_s * 1.7320508f;        // no electron-hole distance exceeds the box diagonal
 
     const bool lab = rp.protocol != MCL_PROTO_SIMULATE;
@@ -643,7 +619,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     int n_slots = n_e;             // electron slots in use (alive or tombstoned)
     int n_fill_alive = 0;          // alive holes in the fill region
     bool ever_filled = false;
-    bool lists_valid = true;       // the candidate lists name the K nearest of ALL holes that were ever alive since they were built
+    bool lists_valid_ = true;      // (REGRID kernels; the others use !ever_filled) the candidate lists name the K nearest of ALL holes that were ever alive since they were built
     bool draws_valid = false;      // stepdraw holds the block of 32 steps that contains rec_i
     int rec_i = 0;
     long long esteps = 0;
@@ -679,7 +655,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     const int fill_cap = max(4, rp.N_e + cfg.fill_extra);
     bool can_regrid = false;       // only replicas with a dosed leg regrid (the launch then has the scratch for it)
     for (int sg = 0; sg < rp.seg_count; sg++) can_regrid |= p.segments[rp.seg_begin + sg].dose_rate != 0.0;
-    can_regrid = can_regrid && cfg.has_regrid;
+    can_regrid = REGRID && can_regrid && cfg.has_regrid;
     auto regrid = [&]() {
         cta_sync<NT>();
         const int n_old = H.n_slots;
@@ -748,7 +724,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             if (nn != NEAR_DEAD) near[sl] = (NearT)hmap[nn];
         }
         H.n_h0 = n_alive; H.n_slots = n_alive; n_fill_alive = 0;
-        lists_valid = false;                       // the lists name old slots
+        lists_valid_ = false;                      // the lists name old slots
         cta_sync<NT>();
     };
     // The KC nearest alive holes of every electron, searched in the grid (after a regrid: all holes).  cr[] / near[] are
@@ -768,7 +744,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             }
         }
         cta_sync<NT>();
-        lists_valid = true;
+        lists_valid_ = true;
     };
 
     for (int sg = 0; sg < rp.seg_count && status == MCL_OK; sg++) {
@@ -825,7 +801,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         set_T(0.0);
         // A dose-free leg after fills (irradiation -> read-out): nothing can be added during the leg, so fresh candidate
         // lists stay exact for all of it and re-targeting is a lookup again instead of a grid search per hit.
-        if (cfg.relist && can_regrid && !lab && !dose_on && ever_filled && !lists_valid && n_e > 0) { regrid(); rebuild_lists(); }
+        bool relist_pending = REGRID && cfg.relist && can_regrid && !lab && !dose_on && ever_filled && !lists_valid_ && n_e > 0;
 
         // The step loop exists twice.  FAST: the simulate protocol without a dose, without per-step records and while no
         // hole was ever added -- what BASELINE-sized ensembles run; protocol, dose, trace and fill-mode branches are compiled
@@ -834,7 +810,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         auto step_loop = [&](auto fast_tag) -> bool {         // true: leg finished (or error), false: continue in the general loop
             constexpr bool FAST = decltype(fast_tag)::value;
             const bool lab_o = lab, iso_o = iso, trace_o = trace, dose_o = dose_on, verify_o = verify_skip;
-            if (FAST) __builtin_assume(!ever_filled);
+            if (FAST) { __builtin_assume(!ever_filled); __builtin_assume(lists_valid_); }
+            // without regrids the lists are exact until the first fill and useless afterwards
+#define lists_valid (REGRID ? lists_valid_ : !ever_filled)
             {
             const bool lab = FAST ? false : lab_o, iso = FAST ? false : iso_o, trace = FAST ? false : trace_o;
             const bool dose_on = FAST ? false : dose_o, verify_skip = FAST ? false : verify_o;
@@ -844,6 +822,16 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 else if (iso) { if (!(obs_idx < rp.obs_count)) break; }
                 else { if (!(t_cur < S.duration)) break; }
                 if (rec_i >= p.max_steps) { status = MCL_ERR_STEPS; break; }
+                if (!FAST && REGRID) {
+                    // the ONE place a regrid happens: before a step that could need a fill-region slot when all fill_cap of them
+                    // hold alive holes, and at the start of a dose-free leg after fills (then the lists are rebuilt as well)
+                    const bool fill_full = can_regrid && dose_on && H.n_slots - H.n_h0 >= fill_cap && n_fill_alive == H.n_slots - H.n_h0;
+                    if (__builtin_expect(fill_full || relist_pending, 0)) {
+                        regrid();
+                        if (relist_pending) rebuild_lists();
+                        relist_pending = false;
+                    }
+                }
 
                 // ---------------- temperature-dependent scalars (uniform; FP32 from an FP64 clock)
                 if (!T_const) set_T(t_cur);
@@ -857,7 +845,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 // A thread owns whole CHUNKS of SPC = 4 slots (chunk b = slots 4b.. belongs to thread b % NT): one 16-byte
                 // load feeds the clocks of a chunk and the post-event scan reads its nearest-hole slots with one load.
                 const int n_chunks = (n_slots + SPC - 1) / SPC;
-                const float A_fast = fmaxf(A1, A2);
+                const float A_fast = fmaxf(A1, A2), dA_ch = A_fast - fminf(A1, A2);
                 auto pair_loop = [&](auto with_cb, auto one_channel) {
                     constexpr bool CB = decltype(with_cb)::value;
                     constexpr bool ONE = decltype(one_channel)::value;     // both tunnelling channels identical
@@ -879,43 +867,46 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         }
 #pragma unroll
                         for (int q = 0; q < NCH; q++) philox4x32_10(w[q][0], w[q][1], w[q][2], w[q][3], K);
+                        // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
+                        auto clock_cb = [&](float le_, float c_, float A_) {
+                            const float a = A_ - c_;
+                            const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
+                            return (le_ - kk) + (c_ - c_);
+                        };
+                        uint32_t tmask = 0u;                               // slots whose tied selector still has to be settled
+                        const float thr0 = best + dA_ch;                   // a tie on the slower channel can gain at most dA_ch
 #pragma unroll
                         for (int q = 0; q < NCH; q++) {
 #pragma unroll
                             for (int k = 0; k < 4; k++) {
                                 const float le = lg2_fast(-lg2_fast(u01(w[q][k])));
-                                float Ak = A1;
-                                bool tie = false;
-                                if (!ONE) {
-                                    const uint32_t sel = w[q][k] & 0x1ffu;
-                                    Ak = sel < sel_T9 ? A2 : A1;
-                                    tie = sel == sel_tie;                  // sel_tie is out of range when Retrap * 512 has no remainder
-                                }
+                                const uint32_t sel = w[q][k] & 0x1ffu;
+                                const float Ak = ONE ? A1 : (sel < sel_cmp ? A2 : A1);
                                 float l;
-                                if (CB) {
-                                    // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
-                                    auto clock_cb = [&](float A_) {
-                                        const float a = A_ - cs[q][k];
-                                        const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
-                                        return (le - kk) + (cs[q][k] - cs[q][k]);
-                                    };
-                                    l = clock_cb(Ak);
-                                    if (!ONE && __builtin_expect(tie, 0)) {
-                                        if (philox_tie_is_ch2((uint32_t)(b0 + q * NT), (uint32_t)rec_i, rid_lo, rid_hi | (DOM_SEL << 28), K.k[0], K.k[1], k, sel_frac))
-                                            l = clock_cb(A2);
-                                    }
-                                } else if (ONE) {
-                                    l = le + cs[q][k];                     // the uniform prefactor A1 is subtracted after the loop
-                                } else {
-                                    const float base = le + cs[q][k];
-                                    l = base - Ak;
-                                    // a tied selector only needs settling if the electron could win with the faster channel
-                                    if (__builtin_expect(tie && base - A_fast < best, 0)) {
-                                        if (philox_tie_is_ch2((uint32_t)(b0 + q * NT), (uint32_t)rec_i, rid_lo, rid_hi | (DOM_SEL << 28), K.k[0], K.k[1], k, sel_frac))
-                                            l = base - A2;
+                                if (CB) l = clock_cb(le, cs[q][k], Ak);
+                                else if (ONE) l = le + cs[q][k];           // the uniform prefactor A1 is subtracted after the loop
+                                else l = (le + cs[q][k]) - Ak;
+                                if (!ONE) tmask |= (sel == sel_tie && l <= thr0) ? (1u << (4 * q + k)) : 0u;
+                                if (l < best) { best = l; bslot = 4 * (b0 + q * NT) + k; }
+                            }
+                        }
+                        if (!ONE && __builtin_expect(tmask != 0u, 0)) {
+                            // rare (2^-9 per slot, and only slots within reach of the running minimum): settle the tie with one more
+                            // word; if it picks the faster channel the clock improves.  Equal clocks go to the smaller slot, as everywhere.
+#pragma unroll
+                            for (int q = 0; q < NCH; q++) {
+#pragma unroll
+                                for (int k = 0; k < 4; k++) {
+                                    if ((tmask >> (4 * q + k)) & 1u) {
+                                        const bool is2 = philox_tie_is_ch2((uint32_t)(b0 + q * NT), (uint32_t)rec_i, rid_lo, rid_hi | (DOM_SEL << 28), K.k[0], K.k[1], k, sel_frac);
+                                        if (is2 == ch2_fast) {
+                                            const float le = lg2_fast(-lg2_fast(u01(w[q][k])));
+                                            const float l2 = CB ? clock_cb(le, cs[q][k], A_fast) : (le + cs[q][k]) - A_fast;
+                                            const int sl2 = 4 * (b0 + q * NT) + k;
+                                            if (l2 < best || (l2 == best && sl2 < bslot)) { best = l2; bslot = sl2; }
+                                        }
                                     }
                                 }
-                                if (l < best) { best = l; bslot = 4 * (b0 + q * NT) + k; }
                             }
                         }
                     };
@@ -1231,13 +1222,12 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 } else if (is_fill) {
                     // ---------------- Box.add_electron (engine.py:133-152), done by warp 0
                     ever_filled = true;
-                    lists_valid = false;
+                    lists_valid_ = false;
                     int es = -1;
                     if (n_e == n_slots) es = n_slots;             // no tombstone to reuse
                     const bool append_e = (es >= 0);
                     if (append_e && es >= cfg.cap_slots - 4) { status = MCL_ERR_CAPACITY; break; }
-                    bool append_h = (n_fill_alive == H.n_slots - H.n_h0);
-                    if (append_h && can_regrid && H.n_slots - H.n_h0 >= fill_cap) regrid();   // fill region full of alive holes: fold it into the grid
+                    const bool append_h = (n_fill_alive == H.n_slots - H.n_h0);       // (a full fill region was folded into the grid at the top of the step)
                     if (append_h && H.n_slots >= p.cap_h) { status = MCL_ERR_CAPACITY; break; }
                     if (warp == 0) {
                         if (!append_e) {
@@ -1291,6 +1281,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             }
             }
             return true;
+#undef lists_valid
         };
         if (!(MCL_FAST_LOOP && cfg.fast && !lab && !trace && !verify_skip && !dose_on && !ever_filled && step_loop(std::true_type{})))
             step_loop(std::false_type{});
@@ -1317,14 +1308,6 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     }
 }
 
-// splitmix-style spreading of the user seed into the two Philox key words
-static inline uint64_t mix64(uint64_t z)
-{
-    z += 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
 
 }  // namespace
 
@@ -1445,18 +1428,29 @@ size_t philox_ws_stride(int cap_e, int cap_h, bool with_regrid)
     return make_plan(cap_e, cap_h, 0, 1 << 30, with_regrid).stride;
 }
 
+template <int NT, int MINB, typename NearT, int PPC, bool SLAB_SMEM, bool REGRID>
+static cudaError_t launch_two(const LaunchParams &p, const RoundKeys &K, const Cfg &cfg, size_t smem, cudaStream_t stream)
+{
+    cudaError_t e = cudaFuncSetAttribute(philox_kernel<NT, MINB, NearT, PPC, SLAB_SMEM, REGRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    philox_kernel<NT, MINB, NearT, PPC, SLAB_SMEM, REGRID><<<p.n_launch, NT, smem, stream>>>(p, K, cfg);
+    return cudaGetLastError();
+}
 template <int NT, int MINB, typename NearT, int PPC, bool SLAB_SMEM = false>
 static cudaError_t launch_one(const LaunchParams &p, const RoundKeys &K, const Cfg &cfg, size_t smem, cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(philox_kernel<NT, MINB, NearT, PPC, SLAB_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    philox_kernel<NT, MINB, NearT, PPC, SLAB_SMEM><<<p.n_replicas, NT, smem, stream>>>(p, K, cfg);
-    return cudaGetLastError();
+    if constexpr (SLAB_SMEM) {
+        return launch_two<NT, MINB, NearT, PPC, true, true>(p, K, cfg, smem, stream);
+    } else {
+        if (p.with_regrid) return launch_two<NT, MINB, NearT, PPC, false, true>(p, K, cfg, smem, stream);
+        return launch_two<NT, MINB, NearT, PPC, false, false>(p, K, cfg, smem, stream);
+    }
 }
 
 cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_slots*/)
 {
-    PhiloxPlan pl = make_plan(p.cap_e, p.cap_h, g_nt_override, p.n_replicas, p.with_regrid != 0);
+    if (p.n_launch <= 0) return cudaSuccess;
+    PhiloxPlan pl = make_plan(p.cap_e, p.cap_h, g_nt_override, p.n_launch, p.with_regrid != 0);
     int fast = 1;
     if (const char *env = getenv("MCL_PHILOX_FAST")) fast = atoi(env) != 0;        // knob: 0 = general step loop only
     int fill_extra = kFillExtra, relist = 1;
@@ -1464,10 +1458,7 @@ cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_
     if (const char *env = getenv("MCL_PHILOX_RELIST")) relist = atoi(env) != 0;    // knob: 0 = read-out legs after fills keep searching the grid
     Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.share_bm, pl.ref_words, pl.off_holes, pl.off_cand, fast,
             pl.off_hpos2, pl.off_hmap, fill_extra, p.with_regrid != 0, relist, pl.sm_hpos, pl.sm_exyz, pl.sm_cstart, pl.sm_cfill};
-    RoundKeys K;
-    uint64_t s = mix64(p.seed);
-    uint32_t k0 = (uint32_t)s, k1 = (uint32_t)(s >> 32);
-    for (int r = 0; r < 10; r++) { K.k[2 * r] = k0; K.k[2 * r + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
+    const RoundKeys K = make_round_keys(p.seed);
     // MINB caps the register count at 64 per thread (32 resident warps per SM when smem allows)
 #define MCL_CASE(NT_, MINB_, PPC_)                                                                  \
     case NT_:                                                                                      \

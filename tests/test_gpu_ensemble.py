@@ -237,6 +237,8 @@ def test_32_bit_nearest_slot_path_gives_identical_results(gpu):
     lt = LabTable(*LAB_CSV["iso"], helpers.DATA_ROOT)
     lab_reps, lab_segs = lt.tables(run)
 
+    os.environ["MCL_SMALLBOX"] = "0"                  # lab rows on the block kernel, which is what has two slot widths
+
     def both():
         a = engine.run_replicas(wl["replicas"], wl["segments"], wl["max_steps"], seed=9, hist=wl["hist"], trace=True, sync=True)
         b = engine.run_replicas(lab_reps, lab_segs, 20000, seed=9, obs_time=lt.obs_time, trace=True, sync=True)
@@ -247,6 +249,7 @@ def test_32_bit_nearest_slot_path_gives_identical_results(gpu):
         a32, b32 = both()
     finally:
         del os.environ["MCL_PHILOX_NEAR32"]
+        del os.environ["MCL_SMALLBOX"]
     for x, y in ((a16, a32), (b16, b32)):
         x.raise_on_error(); y.raise_on_error()
         assert np.array_equal(x.event, y.event) and np.array_equal(x.n_e, y.n_e) and np.array_equal(x.t, y.t)
@@ -326,6 +329,16 @@ def test_shared_memory_slab_changes_no_result(gpu, capsys):
     from mcluminescence_b200.workloads import c4_candidates
     cfg = compose(overrides=helpers.LAB_OVERRIDES)
     P = c4_candidates(64, seed=9)
+    os.environ["MCL_SMALLBOX"] = "0"                  # this test is about the block kernel's two slab placements
+    try:
+        _slab_equality(P, cfg, optimizer)
+    finally:
+        del os.environ["MCL_SMALLBOX"]
+    capsys.readouterr()
+
+
+def _slab_equality(P, cfg, optimizer):
+    import os
     for exp in ("tl_clbr", "iso"):
         for extra in (None, "-92"):
             if extra is not None:
@@ -340,4 +353,39 @@ def test_shared_memory_slab_changes_no_result(gpu, capsys):
             finally:
                 os.environ.pop("MCL_PHILOX_FILL_EXTRA", None)
             assert np.array_equal(a, b) and ea == eb, (exp, extra)
-    capsys.readouterr()
+
+
+def test_smallbox_kernel_traces_are_consistent(gpu):
+    """The one-warp-per-replica kernel of the Optimizer path: its per-step records must be consistent with its summary
+    outputs (charge bookkeeping with fills and recombinations, electron-steps, observation crossings), must not depend
+    on whether records are requested, nor on the batch a replica runs in."""
+    from mcluminescence_b200 import engine
+    from mcluminescence_b200.config import compose, initialize_runs
+    from mcluminescence_b200.replicas import LAB_CSV, LabTable
+    run = initialize_runs(compose(overrides=helpers.LAB_OVERRIDES))[0]
+    for exp in ("tl_clbr", "iso"):
+        lt = LabTable(*LAB_CSV[exp], helpers.DATA_ROOT)
+        reps1, segs = lt.tables(run)
+        M, n_rows = 8, len(reps1)
+        reps = np.tile(reps1, M)
+        obs_time = np.tile(lt.obs_time, M)
+        if lt.obs_time.size:
+            for m in range(M):
+                reps["obs_begin"][m * n_rows:(m + 1) * n_rows] += m * len(lt.obs_time)
+        tr = engine.run_replicas(reps, segs, 20000, seed=61, obs_time=obs_time, trace=True, sync=True)
+        fin = engine.run_replicas(reps, segs, 20000, seed=61, obs_time=obs_time, trace=False, sync=True)
+        tr.raise_on_error(); fin.raise_on_error()
+        assert np.array_equal(tr.final_n_e, fin.final_n_e) and np.array_equal(tr.esteps, fin.esteps)
+        assert np.array_equal(tr.steps_used, fin.steps_used) and np.array_equal(tr.obs_n_e, fin.obs_n_e)
+        part = engine.run_replicas(reps[n_rows:3 * n_rows], segs, 20000, seed=61, replica_id0=n_rows, trace=False, sync=True,
+                                   obs_time=obs_time[:max(1, 2 * len(lt.obs_time))] if lt.obs_time.size else None) if not lt.obs_time.size else None
+        if part is not None:
+            assert np.array_equal(part.final_n_e, fin.final_n_e[n_rows:3 * n_rows])
+        for r in range(len(reps)):
+            n = int(tr.steps_used[r])
+            ne, ev, t = tr.n_e[r, :n].astype(np.int64), tr.event[r, :n], tr.t[r, :n]
+            before = np.concatenate([[int(reps["n_e0"][r])], ne[:-1]])
+            assert np.all((ne - before == 1) | ((ne - before == -1) & (ev == 1)))      # a step adds a pair or removes one
+            assert np.all(ev[ne - before == 1] == 0) and np.all(np.diff(t) >= 0)
+            assert int(before.sum()) == int(tr.esteps[r]) and int(ne[-1]) == int(tr.final_n_e[r])
+            assert ne.max() <= int(reps["N_e"][r]) + 1

@@ -110,11 +110,15 @@ def test_results_depend_only_on_seed_and_global_replica_id(gpu):
     assert not np.array_equal(other.event, part.event)
 
 
-@pytest.mark.parametrize("exp,knobs", [("tl_clbr", {}), ("iso", {}),
-                                       # regrid as soon as 8 fill-region slots are in use (default: N_e + 64): dozens of regrids per row
-                                       ("tl_clbr", {"MCL_PHILOX_FILL_EXTRA": "-92"}), ("iso", {"MCL_PHILOX_FILL_EXTRA": "-92"}),
-                                       # hole tables in the HBM slab instead of shared memory
-                                       ("tl_clbr", {"MCL_PHILOX_SMEM_SLAB": "0"})])
+BLOCK = {"MCL_SMALLBOX": "0"}           # lab rows on the block kernel instead of the one-warp-per-replica kernel
+
+
+@pytest.mark.parametrize("exp,knobs", [("tl_clbr", {}), ("iso", {}), ("tl_fsm-13", {}),
+                                       ("tl_clbr", BLOCK), ("iso", BLOCK),
+                                       # block kernel, regrid as soon as 8 fill-region slots are in use (default: N_e + 64): dozens of regrids per row
+                                       ("tl_clbr", dict(BLOCK, MCL_PHILOX_FILL_EXTRA="-92")), ("iso", dict(BLOCK, MCL_PHILOX_FILL_EXTRA="-92")),
+                                       # block kernel, hole tables in the HBM slab instead of shared memory
+                                       ("tl_clbr", dict(BLOCK, MCL_PHILOX_SMEM_SLAB="0"))])
 def test_lab_protocol_ensemble_matches_oracle(gpu, exp, knobs, monkeypatch):
     """TL_lab / ISO_lab with fills, stale caches and the conduction-band channel."""
     from mcluminescence_b200 import engine
