@@ -16,6 +16,7 @@ from .config import physics_record
 PROTO_SIMULATE = 0
 PROTO_TL_LAB = 1
 PROTO_ISO_LAB = 2
+PROTO_TL_LEGACY = 3          # pre-refactor TL loop (reference src/est_params/functions.py:270-360), see legacy_box_geometry
 
 MODE_PHILOX = 0
 MODE_REPLAY = 1
@@ -56,10 +57,30 @@ def box_geometry(mc: Mapping[str, Any], phys: Mapping[str, Any],
     return float(side), int(mc["N_e"]), e0, total_h
 
 
+def legacy_box_geometry(mc: Mapping[str, Any], phys: Mapping[str, Any],
+                        e_ratio_start: Optional[float]) -> Tuple[float, int, int, int]:
+    """(side, N_e, n_e0, n_h0) as the LEGACY ``initialize_box_bg`` computes them
+    (``src/est_params/functions.py:51-80``): the boundary shell adds ``int(density * (V_b - V))`` holes to
+    ``int(holes)`` instead of ``int(holes * bf**3)``; same expressions, same operation order."""
+    e0 = int(mc["N_e"] * (e_ratio_start if e_ratio_start is not None else 0))      # :57
+    rho = mc["rho_prime"] * (3 / (4 * np.pi) * phys["alpha"] ** 3)                  # :82-86
+    h = int(mc["holes"])                                                              # :60
+    d = (h / rho) ** (1 / 3)                                                          # :61
+    box_l, box_w, box_h = d, d, d
+    b_factor = mc["boundary_factor"]
+    box_l_b, box_w_b, box_h_b = box_l * b_factor, box_w * b_factor, box_h * b_factor
+    box_volume = box_l * box_w * box_h
+    box_volume_b = box_l_b * box_w_b * box_h_b
+    holes_density = h / (box_l * box_w * box_h)
+    holes_boundary_n = int(holes_density * (box_volume_b - box_volume))               # :74-76
+    return float(d), int(mc["N_e"]), e0, h + holes_boundary_n
+
+
 def fill_replica(rec: np.void, mc: Mapping[str, Any], phys_node: Mapping[str, Any],
                  e_ratio_start: Optional[float], protocol: int) -> None:
     phys = physics_record(phys_node)                 # TypeError on unknown keys, like Physics(**...)
-    side, N_e, e0, n_h0 = box_geometry(mc, phys, e_ratio_start)
+    geometry = legacy_box_geometry if protocol == PROTO_TL_LEGACY else box_geometry
+    side, N_e, e0, n_h0 = geometry(mc, phys, e_ratio_start)
     for k in ("alpha", "b", "s", "E_cb", "E_loc_1", "E_loc_2", "D0", "Retrap", "k_b"):
         rec[k] = float(phys[k])
     rec["side"] = side
@@ -167,16 +188,19 @@ class LabTable:
             self.exp_no = np.asarray(exps)
         self.n_rows = n
 
-    def tables(self, run_cfg: Mapping[str, Any]):
-        """Replica/segment tables for ONE parameter set: ``n_rows`` replicas."""
+    def tables(self, run_cfg: Mapping[str, Any], legacy: bool = False):
+        """Replica/segment tables for ONE parameter set: ``n_rows`` replicas.  ``legacy`` (TL only): the pre-refactor
+        semantics of ``src/est_params/functions.py`` (protocol ``PROTO_TL_LEGACY``)."""
         mc, phys_node = run_cfg["exp_type_fp"], run_cfg["physics_fp"]
         reps = np.zeros(self.n_rows, dtype=REPLICA_DTYPE)
         segs = self.segments.copy()
+        if legacy and self.protocol != PROTO_TL_LAB:
+            raise ValueError("legacy semantics exist for the TL lab protocol only")
         if self.protocol == PROTO_TL_LAB:
             D = physics_record(phys_node)["D"]            # tl_trap_lab.py:83
             segs["dose_rate"] = float(D)                  # TypeError on None, like `D == 0` would not
         for k in range(self.n_rows):
-            fill_replica(reps[k], mc, phys_node, float(self.e_ratio_start[k]), self.protocol)
+            fill_replica(reps[k], mc, phys_node, float(self.e_ratio_start[k]), PROTO_TL_LEGACY if legacy else self.protocol)
             reps[k]["seg_begin"] = k
             reps[k]["obs_begin"] = self.obs_begin[k]
             reps[k]["obs_count"] = self.obs_begin[k + 1] - self.obs_begin[k]

@@ -42,6 +42,7 @@
 #define MCLO_PROTO_SIMULATE 0
 #define MCLO_PROTO_TL_LAB   1
 #define MCLO_PROTO_ISO_LAB  2
+#define MCLO_PROTO_TL_LEGACY 3  /* pre-refactor TL loop: src/est_params/functions.py:270-360 (see run_legacy_tl below) */
 
 #define MCLO_OK              0
 #define MCLO_ERR_STEPS      -1   /* replica needs more than max_steps records (reference: IndexError) */
@@ -338,6 +339,81 @@ static inline void wait_min(const box_t *bx, double *mn, int *arg, int *any)
     *mn = best; *arg = bi; *any = a;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Legacy (pre-refactor) semantics: src/est_params/functions.py, the code that produced         */
+/* results/lab_sims/result_*.csv.  Pinned by tests/golden/legacy_*.npz, generated from the      */
+/* UNMODIFIED legacy function sim_lab_TL_residuals (oracle/ref_harness/gen_golden.py).          */
+/* ------------------------------------------------------------------------------------------ */
+/* functions.py:138-148 -- lifetime D0/D*1/(N-e), 1e20 when full or D == 0; always one uniform */
+static double legacy_filling_time(const box_t *bx, const mclo_replica *rp, double D, mclo_rng *rng)
+{
+    double lifetime;
+    if (bx->n_e == rp->N_e || D == 0.0) lifetime = 1e20;
+    else lifetime = rp->D0 / D * 1 / (double)(rp->N_e - bx->n_e);
+    return rng_exponential(rng, lifetime);
+}
+
+/* functions.py:115-136 -- ONE channel draw per call (`rand(1) > Retrap` -> E_loc_1), then one exponential per electron */
+static void legacy_lifetimes(box_t *bx, const mclo_replica *rp, double T, mclo_rng *rng)
+{
+    double kT = rp->k_b * T;
+    double k_cb = rp->s * exp(-rp->E_cb / kT);
+    double u = rng_uniform(rng);
+    double E_loc = (u > rp->Retrap) ? rp->E_loc_1 : rp->E_loc_2;
+    for (int i = 0; i < bx->n_e; i++)
+        bx->wait[i] = 1.0 / (k_cb + rp->b * exp(-E_loc / kT - rp->alpha * bx->min_d[i]));
+    for (int i = 0; i < bx->n_e; i++) bx->wait[i] = rng_exponential(rng, bx->wait[i]);
+}
+
+/* functions.py:214-228 + 150-161 + 104-113: append a pair, then EVERY electron's nearest hole is exact again
+ * (the new electron sees its twin hole too; np.argmin keeps the old hole on an exact tie) */
+static int legacy_add_electron(box_t *bx, const mclo_replica *rp, mclo_rng *rng)
+{
+    double core = rp->side, bnd = rp->side * rp->boundary_factor;
+    if (bx->n_e + 1 > bx->cap_e) { int rc = box_grow_electrons(bx); if (rc) return rc; }
+    if (bx->n_h + 1 > bx->cap_h) { int rc = box_grow_holes(bx); if (rc) return rc; }
+    double x = rng_uniform(rng) * core, y = rng_uniform(rng) * core, z = rng_uniform(rng) * core;
+    double hx = rng_uniform(rng) * bnd, hy = rng_uniform(rng) * bnd, hz = rng_uniform(rng) * bnd;
+    int e = bx->n_e, h = bx->n_h;
+    bx->ex[e] = x; bx->ey[e] = y; bx->ez[e] = z;
+    bx->hx[h] = hx; bx->hy[h] = hy; bx->hz[h] = hz;
+    bx->n_e++; bx->n_h++;
+    for (int i = 0; i < e; i++) {
+        double d = dist(bx->ex[i], bx->ey[i], bx->ez[i], hx, hy, hz);
+        if (d < bx->min_d[i]) { bx->min_d[i] = d; bx->nearest[i] = h; }
+    }
+    return scan_nearest(bx, x, y, z, bx->n_h, &bx->min_d[e], &bx->nearest[e]);
+}
+
+/* functions.py:241-261 with :176-199,201-212.  `np.where(time >= recombination + e_timer)[0]` broadcasts against the
+ * default e_timer of shape (1,1), so the ROW indices it returns are all zero: whatever the waiting times say, the
+ * electron that recombines is electron 0 (the oldest), with its cached hole.  Electrons that shared the hole re-scan. */
+static int legacy_remove_first(box_t *bx)
+{
+    int ne = bx->n_e, nh = bx->n_h;
+    int h = bx->nearest[0];
+    memmove(bx->ex, bx->ex + 1, (size_t)(ne - 1) * sizeof(double));
+    memmove(bx->ey, bx->ey + 1, (size_t)(ne - 1) * sizeof(double));
+    memmove(bx->ez, bx->ez + 1, (size_t)(ne - 1) * sizeof(double));
+    memmove(bx->min_d, bx->min_d + 1, (size_t)(ne - 1) * sizeof(double));
+    memmove(bx->nearest, bx->nearest + 1, (size_t)(ne - 1) * sizeof(int32_t));
+    size_t th = (size_t)(nh - 1 - h);
+    memmove(bx->hx + h, bx->hx + h + 1, th * sizeof(double));
+    memmove(bx->hy + h, bx->hy + h + 1, th * sizeof(double));
+    memmove(bx->hz + h, bx->hz + h + 1, th * sizeof(double));
+    bx->n_e = --ne; bx->n_h = --nh;
+    /* the electrons to refresh were selected BEFORE the shift (electrons_new_distances): exactly those cached on h */
+    for (int i = 0; i < ne; i++) {
+        if (bx->nearest[i] == h) {
+            int rc = scan_nearest(bx, bx->ex[i], bx->ey[i], bx->ez[i], nh, &bx->min_d[i], &bx->nearest[i]);
+            if (rc) return rc;
+        } else if (bx->nearest[i] > h) {
+            bx->nearest[i]--;
+        }
+    }
+    return MCLO_OK;
+}
+
 /* Per-replica outputs (all caller-allocated, row r at offset r*max_steps) */
 typedef struct {
     int32_t *event;      /* [R,max_steps] 1 = recombination (Lum), 0 otherwise              */
@@ -376,7 +452,47 @@ static int run_one(const mclo_replica *rp, const mclo_segment *segs, const doubl
     rc = box_seed(&bx, rp, rng);
     if (rc) goto done;
 
-    if (rp->protocol == MCLO_PROTO_SIMULATE) {
+    if (rp->protocol == MCLO_PROTO_TL_LEGACY) {
+        /* src/est_params/functions.py:289-349 (sim_lab_TL_residuals, one lab row, one replica) */
+        const mclo_segment *S = &segs[rp->seg_begin];
+        double D = S->dose_rate, T = S->T_start + 273.15, t_cur = 0.0;
+        double dt_filling = legacy_filling_time(&bx, rp, D, rng);
+        if (bx.n_e > 0 && bx.n_h > 0) legacy_lifetimes(&bx, rp, T, rng);      /* `if distances.size != 0` */
+        while (t_cur < S->duration) {
+            double wmin; int arg, any;
+            wait_min(&bx, &wmin, &arg, &any);
+            double dt_recomb = bx.n_e > 0 ? wmin : dt_filling;
+            double dt = dt_recomb < dt_filling ? dt_recomb : dt_filling;
+            if (i >= max_steps) { rc = MCLO_ERR_STEPS; break; }
+            esteps += bx.n_e;
+            int ev = 0, kd, ei, hi;
+            if (dt == dt_filling) {
+                if (dt < 0) dt = 0;
+                T = T + dt * S->T_rate;
+                t_cur = t_cur + dt;
+                ei = bx.n_e; hi = bx.n_h; kd = 1;
+                rc = legacy_add_electron(&bx, rp, rng);
+                if (rc) break;
+                legacy_lifetimes(&bx, rp, T, rng);
+                dt_filling = legacy_filling_time(&bx, rp, D, rng);
+            } else {
+                if (dt < 0) dt = 0;
+                T = T + dt * S->T_rate;
+                t_cur = t_cur + dt;
+                ei = 0; hi = bx.nearest[0]; kd = 2; ev = 1;
+                rc = legacy_remove_first(&bx);
+                if (rc) break;
+                if (rng_uniform(rng) < rp->Retrap) {            /* functions.py:328-331: re-trapping adds a fresh pair */
+                    rc = legacy_add_electron(&bx, rp, rng);
+                    if (rc) break;
+                }
+                legacy_lifetimes(&bx, rp, T, rng);
+                dt_filling = legacy_filling_time(&bx, rp, D, rng);
+            }
+            REC(out, r, i, ev, kd, ei, hi, bx.n_e, t_cur);
+            i++;
+        }
+    } else if (rp->protocol == MCLO_PROTO_SIMULATE) {
         /* simulate.py:46-92, one pass per schedule segment (the reference has exactly one) */
         double t_off = 0.0;
         for (int sg = 0; sg < rp->seg_count && !rc; sg++) {

@@ -156,6 +156,24 @@ def main():
         if want(name):
             manifest[f"lab_{name}"] = save_lab_case(name, exp, seed, p)
 
+    # legacy (pre-refactor) TL code, src/est_params/functions.py: what produced results/lab_sims/result_tl_clbr.csv
+    legacy_cases = [("default", None, 3), ("default_b", None, 4), ("best_row", bp, 3), ("best_row_b", bp, 5),
+                    ("sobol0", cand[0], 300), ("sobol1", cand[1], 301), ("sobol2", cand[2], 302)]
+    for name, p, seed in legacy_cases:
+        if want("legacy_" + name):
+            t0 = time.time()
+            try:
+                res = refrun.run_legacy_tl(p, seed)
+            except Exception as exc:  # noqa: BLE001  (a candidate the legacy code itself cannot finish)
+                print("legacy", name, "failed in the reference:", type(exc).__name__, exc)
+                continue
+            np.savez_compressed(os.path.join(GOLD, f"legacy_{name}.npz"), rows=res["rows"],
+                                p=np.asarray(p if p is not None else [], dtype=np.float64))
+            manifest[f"legacy_{name}"] = dict(kind="legacy_tl", seed=seed, value=res["value"],
+                                              p=[float(v) for v in p] if p is not None else None,
+                                              wall_s=round(time.time() - t0, 2))
+            print("legacy", name, repr(res["value"]), res["rows"][:, 2:].sum(0), manifest[f"legacy_{name}"]["wall_s"], "s")
+
     # SURVEY KAT-0: the shipped default config (TL12 + basicTL12), ~3 minutes on one core
     if not args.skip_kat0 and want("kat0"):
         manifest["sim_kat0"] = save_sim_case("kat0", [], 12345)

@@ -151,3 +151,98 @@ def run_lab(exp: str, seed: int,
         with redirect_stdout(buf):
             val = m["optimizer"].run_one_sim(cfg, exp)
     return dict(value=float(val), rec=rec, printed=buf.getvalue())
+
+
+# ---------------------------------------------------------------------------------------
+# Legacy (pre-refactor) code: src/est_params/functions.py, which produced results/lab_sims/*.csv
+# ---------------------------------------------------------------------------------------
+_legacy = {}
+
+
+def load_legacy():
+    """Import the reference's UNMODIFIED legacy module ``src/est_params/functions.py`` (once)."""
+    if _legacy:
+        return _legacy["F"]
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    import importlib.util
+    for p in (os.path.join(_HERE, "shims"), _REPO):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    # the legacy package has its own `paths` module with the same name as src/class/paths.py: load both explicitly
+    d = os.path.join(REFERENCE_ROOT, "src", "est_params")
+    saved = sys.modules.pop("paths", None)
+    sys.path.insert(0, d)
+    try:
+        spec = importlib.util.spec_from_file_location("mcl_legacy_functions", os.path.join(d, "functions.py"))
+        F = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(F)
+    finally:
+        sys.path.remove(d)
+        sys.modules.pop("paths", None)
+        if saved is not None:
+            sys.modules["paths"] = saved
+    _legacy["F"] = F
+    return F
+
+
+def run_legacy_tl(p, seed: int, lab_data: str = "CLBR_IRSL50_0.25KperGy",
+                  overrides: Sequence[str] = ("exp_type_fp=TLlab", "physics_fp=lab_TL")):
+    """``np.random.seed(seed); sim_lab_TL_residuals(run_cfg, lab_data)`` on the genuine legacy code, with the number
+    of electron additions / recombinations / uniforms per lab row captured by wrapping its helpers."""
+    import io
+    from contextlib import redirect_stdout
+    from mcluminescence_b200.config import initialize_runs
+    from mcluminescence_b200.optimizer import cfg_with_params
+    F = load_legacy()
+    cfg = compose(list(overrides))
+    if p is not None:
+        cfg = cfg_with_params(cfg, np.asarray(p, dtype=float))
+    run = initialize_runs(cfg)[0]
+    rows = []                       # per lab row: [e0, holes_n, adds, recombinations, uniforms]
+    o_init, o_add, o_rec = F.initialize_box_bg, F.add_electron, F.recomber
+    o_rand, o_exp = np.random.rand, np.random.exponential
+
+    def init(cfg_, e_ratio_start=0):
+        e, h, dim = o_init(cfg_, e_ratio_start)
+        rows.append([e.shape[0], h.shape[0], 0, 0, 0])
+        rows[-1][4] += 3 * (e.shape[0] + h.shape[0])         # drawn inside o_init through the wrapped rand
+        return e, h, dim
+
+    def add(*a, **k):
+        rows[-1][2] += 1
+        return o_add(*a, **k)
+
+    def rec(*a, **k):
+        rows[-1][3] += 1
+        return o_rec(*a, **k)
+
+    def rand(*shape):
+        if rows and not _in_init[0]:
+            rows[-1][4] += int(np.prod(shape)) if shape else 1
+        return o_rand(*shape)
+
+    def exponential(scale=1.0, size=None):
+        if rows:
+            rows[-1][4] += int(np.size(scale)) if size is None else int(np.prod(size))
+        return o_exp(scale, size)
+
+    _in_init = [False]
+
+    def init_guarded(cfg_, e_ratio_start=0):
+        _in_init[0] = True
+        try:
+            return init(cfg_, e_ratio_start)
+        finally:
+            _in_init[0] = False
+
+    F.initialize_box_bg, F.add_electron, F.recomber = init_guarded, add, rec
+    np.random.rand, np.random.exponential = rand, exponential
+    try:
+        np.random.seed(seed)
+        with redirect_stdout(io.StringIO()):
+            val = F.sim_lab_TL_residuals(run, lab_data)
+    finally:
+        F.initialize_box_bg, F.add_electron, F.recomber = o_init, o_add, o_rec
+        np.random.rand, np.random.exponential = o_rand, o_exp
+    return dict(value=float(val), rows=np.asarray(rows, dtype=np.int64))

@@ -63,6 +63,19 @@ def lab_setup(meta):
     return lt, reps, segs, run
 
 
+def legacy_setup(meta):
+    """(LabTable, replicas, segments, run_cfg) for a golden case of the LEGACY TL code (protocol PROTO_TL_LEGACY)."""
+    from mcluminescence_b200.optimizer import cfg_with_params
+    cfg = compose(overrides=LAB_OVERRIDES)
+    if meta["p"] is not None:
+        cfg = cfg_with_params(cfg, np.asarray(meta["p"], dtype=float))
+    run = initialize_runs(cfg)[0]
+    csv, proto = LAB_CSV["tl_clbr"]
+    lt = LabTable(csv, proto, DATA_ROOT)
+    reps, segs = lt.tables(run, legacy=True)
+    return lt, reps, segs, run
+
+
 def log_from_result(res, r_list):
     """Structural log rows (kind, e_idx, h_idx) with kind 1 fill / 2 recombination, replica order."""
     rows = []
