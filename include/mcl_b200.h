@@ -30,6 +30,10 @@ extern "C" {
 #define MCL_PROTO_SIMULATE 0   /* src/class/simulate.py:46-92  (dt cap, `.any()` rule, Lum record) */
 #define MCL_PROTO_TL_LAB   1   /* src/class/tl_trap_lab.py:75-111 (one lab row)                     */
 #define MCL_PROTO_ISO_LAB  2   /* src/class/tl_trap_lab.py:135-172 (one isothermal experiment)      */
+#define MCL_PROTO_TL_LEGACY 3  /* src/est_params/functions.py:270-360: the PRE-REFACTOR TL row loop that produced
+                                  results/lab_sims/result_*.csv (one channel draw per step, exact caches after a fill,
+                                  the oldest electron recombines, re-trapping re-adds a pair).  Boxes of <= 124 traps,
+                                  native mode, no histograms; n_h0 = int(holes) + int(density * (V_b - V))            */
 
 /* random-number modes */
 #define MCL_MODE_PHILOX 0      /* native: Philox4x32-10 keyed (seed, replica), counter (slot, step); FP32 + SFU */
@@ -158,8 +162,9 @@ typedef struct mcl_lab {
     const double *target;          /* HOST: TL [n_rows] Fill; ISO [n_obs] e_ratio                   */
     double N_e, boundary_factor, D, k_b;  /* fixed experiment fields (TLlab.yaml / lab_TL.yaml)    */
     int32_t max_steps;
-    int32_t reserved;
+    int32_t flags;                 /* bit 0: legacy est_params semantics (TL only; MCL_PROTO_TL_LEGACY)   */
 } mcl_lab;
+#define MCL_LAB_LEGACY 1
 int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uint64_t seed,
                   uint64_t candidate_id0, double *mse, int64_t *esteps_total, void *stream);
 /* mcl_objective keeps its (multi-GB) device scratch between calls (per device, grow-only) and is

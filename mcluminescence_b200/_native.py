@@ -48,7 +48,7 @@ class Lab(C.Structure):
         ("rows", C.c_void_p), ("e_ratio_start", C.c_void_p), ("obs_begin", C.c_void_p),
         ("obs_time", C.c_void_p), ("target", C.c_void_p),
         ("N_e", C.c_double), ("boundary_factor", C.c_double), ("D", C.c_double), ("k_b", C.c_double),
-        ("max_steps", C.c_int32), ("reserved", C.c_int32),
+        ("max_steps", C.c_int32), ("flags", C.c_int32),
     ]
 
 

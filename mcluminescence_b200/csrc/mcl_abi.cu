@@ -63,7 +63,10 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
     for (int r = 0; r < a->n_replicas; r++) {
         const mcl_replica &rp = a->replicas[r];
         if (rp.N_e < 0 || rp.n_e0 < 0 || rp.n_h0 < 0) { set_error("replica %d: negative sizes", r); return MCL_ERR_ARG; }
-        if (rp.protocol < MCL_PROTO_SIMULATE || rp.protocol > MCL_PROTO_ISO_LAB) { set_error("replica %d: bad protocol %d", r, rp.protocol); return MCL_ERR_ARG; }
+        if (rp.protocol < MCL_PROTO_SIMULATE || rp.protocol > MCL_PROTO_TL_LEGACY) { set_error("replica %d: bad protocol %d", r, rp.protocol); return MCL_ERR_ARG; }
+        if (rp.protocol == MCL_PROTO_TL_LEGACY && !(small_ok && smallbox_eligible(rp))) {
+            set_error("replica %d: the legacy TL semantics exist for native-mode boxes of at most 124 traps without histograms", r); return MCL_ERR_ARG;
+        }
         if (rp.seg_count < 1 || rp.seg_begin < 0 || rp.seg_begin + rp.seg_count > a->n_segments) {
             set_error("replica %d: segment range [%d,%d) outside table of %d", r, rp.seg_begin, rp.seg_begin + rp.seg_count, a->n_segments);
             return MCL_ERR_ARG;
@@ -103,11 +106,29 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
     L->off_order = o; o = align_up(o + sizeof(int32_t) * (size_t)a->n_replicas, 256);
     L->off_slabs = o; o += L->stride * L->big.size();
     if (a->mode == MCL_MODE_PHILOX) {
+        // longest expected work first.  Populations have a handful of distinct weights (one per lab row), ensembles one:
+        // a counting sort over the distinct values; a comparison sort only when there are many.
         std::vector<double> w((size_t)a->n_replicas);
-        for (int r = 0; r < a->n_replicas; r++) w[r] = work_estimate(a, a->replicas[r]);
-        auto by_work = [&](int32_t x, int32_t y) { return w[x] > w[y]; };
-        std::stable_sort(L->small.begin(), L->small.end(), by_work);
-        std::stable_sort(L->big.begin(), L->big.end(), by_work);
+        std::vector<double> distinct;
+        for (int r = 0; r < a->n_replicas; r++) {
+            w[r] = work_estimate(a, a->replicas[r]);
+            if (distinct.size() <= 64 && std::find(distinct.begin(), distinct.end(), w[r]) == distinct.end()) distinct.push_back(w[r]);
+        }
+        auto order_list = [&](std::vector<int32_t> &list) {
+            if (distinct.size() <= 1 || list.size() < 2) return;
+            if (distinct.size() > 64) {
+                std::stable_sort(list.begin(), list.end(), [&](int32_t x, int32_t y) { return w[x] > w[y]; });
+                return;
+            }
+            std::vector<double> d(distinct);
+            std::sort(d.begin(), d.end(), std::greater<double>());
+            std::vector<std::vector<int32_t>> bucket(d.size());
+            for (int32_t r : list) bucket[std::find(d.begin(), d.end(), w[r]) - d.begin()].push_back(r);
+            size_t o2 = 0;
+            for (auto &b : bucket) for (int32_t r : b) list[o2++] = r;
+        };
+        order_list(L->small);
+        order_list(L->big);
     }
     L->total = o;
     return MCL_OK;
@@ -119,11 +140,15 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
         if (_e != cudaSuccess) { set_error("%s: %s", #x, cudaGetErrorString(_e)); return MCL_ERR_CUDA; } \
     } while (0)
 
-static int run_device(const mcl_run_args *a, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr)
+static int run_device(const mcl_run_args *a, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr, const Layout *planned = nullptr)
 {
-    Layout L;
-    int rc = plan_layout(a, &L);
-    if (rc) return rc;
+    Layout L_own;
+    if (!planned) {
+        int rc = plan_layout(a, &L_own);
+        if (rc) return rc;
+        planned = &L_own;
+    }
+    const Layout &L = *planned;
     if (!a->workspace || a->workspace_bytes < L.total) {
         set_error("mcl_run: workspace too small (%zu < %zu)", a->workspace_bytes, L.total); return MCL_ERR_ARG;
     }
@@ -180,6 +205,23 @@ static int run_device(const mcl_run_args *a, cudaEvent_t ev0 = nullptr, cudaEven
 }
 
 int mcl_run_timed(const mcl_run_args *a, void *ev0, void *ev1) { return run_device(a, (cudaEvent_t)ev0, (cudaEvent_t)ev1); }
+
+// plan once, then allocate and run: what mcl_objective does (planning a population of 45 000 replicas takes milliseconds)
+struct PlannedRun { Layout L; };
+PlannedRun *mcl_plan(const mcl_run_args *a, size_t *bytes)
+{
+    PlannedRun *pr = new PlannedRun;
+    if (plan_layout(a, &pr->L)) { delete pr; return nullptr; }
+    *bytes = pr->L.total;
+    return pr;
+}
+int mcl_run_planned(const mcl_run_args *a, PlannedRun *pr, void *ev0, void *ev1)
+{
+    const int rc = run_device(a, (cudaEvent_t)ev0, (cudaEvent_t)ev1, &pr->L);
+    delete pr;
+    return rc;
+}
+void mcl_plan_discard(PlannedRun *pr) { delete pr; }
 
 }  // namespace mcl
 

@@ -43,7 +43,11 @@ struct LaunchParams {
 constexpr int kFillExtra = 64;
 
 void set_error(const char *fmt, ...);
-int mcl_run_timed(const mcl_run_args *a, void *ev0, void *ev1);   // mcl_run with CUDA events recorded around the kernel launch
+int mcl_run_timed(const mcl_run_args *a, void *ev0, void *ev1);
+struct PlannedRun;
+PlannedRun *mcl_plan(const mcl_run_args *a, size_t *bytes);                      // nullptr on error (mcl_last_error)
+int mcl_run_planned(const mcl_run_args *a, PlannedRun *pr, void *ev0, void *ev1);   // consumes pr
+void mcl_plan_discard(PlannedRun *pr);   // mcl_run with CUDA events recorded around the kernel launch
 
 // kernels' host launchers (defined in the .cu files)
 cudaError_t launch_replay(const LaunchParams &p, cudaStream_t stream);

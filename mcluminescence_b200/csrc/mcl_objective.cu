@@ -87,6 +87,8 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
     if (lab->protocol != MCL_PROTO_TL_LAB && lab->protocol != MCL_PROTO_ISO_LAB) { set_error("mcl_objective: protocol must be TL_LAB or ISO_LAB"); return MCL_ERR_ARG; }
     if (lab->n_rows <= 0 || !lab->rows || !lab->e_ratio_start || !lab->target) { set_error("mcl_objective: lab table incomplete"); return MCL_ERR_ARG; }
     const bool iso = lab->protocol == MCL_PROTO_ISO_LAB;
+    const bool legacy = (lab->flags & MCL_LAB_LEGACY) != 0;
+    if (legacy && iso) { set_error("mcl_objective: legacy semantics exist for the TL protocol only"); return MCL_ERR_ARG; }
     if (iso && (!lab->obs_begin || !lab->obs_time)) { set_error("mcl_objective: ISO needs obs_begin / obs_time"); return MCL_ERR_ARG; }
     const int n_rows = lab->n_rows;
     const int n_obs = iso ? lab->obs_begin[n_rows] : 0;
@@ -112,16 +114,27 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
                      retrap = P[9 * (size_t)S + c];
         const double rho = rho_prime * (3.0 / (4.0 * M_PI) * pow(alpha, 3.0));     // tl_trap_lab.py:33
         const double side = pow(holes / rho, 1.0 / 3.0);                              // :34
-        const int n_h0 = (int)(holes * pow(lab->boundary_factor, 3.0));               // engine.py:127
+        int n_h0 = (int)(holes * pow(lab->boundary_factor, 3.0));                     // engine.py:127
+        double side_c = side;
+        if (legacy) {
+            // initialize_box_bg (src/est_params/functions.py:51-80), same operation order as the Python expressions
+            const int h = (int)holes;
+            const double d = pow((double)h / rho, 1.0 / 3.0);
+            const double lb_ = d * lab->boundary_factor;
+            const double vol = d * d * d, vol_b = lb_ * lb_ * lb_;
+            const double density = (double)h / (d * d * d);
+            n_h0 = h + (int)(density * (vol_b - vol));
+            side_c = d;
+        }
         for (int k = 0; k < n_rows; k++) {
             mcl_replica &rp = reps[(size_t)c * n_rows + k];
             rp.alpha = alpha; rp.b = b; rp.s = s; rp.E_cb = E_cb; rp.E_loc_1 = E1; rp.E_loc_2 = E2;
-            rp.D0 = D0; rp.Retrap = retrap; rp.k_b = lab->k_b; rp.side = side;
+            rp.D0 = D0; rp.Retrap = retrap; rp.k_b = lab->k_b; rp.side = side_c;
             rp.boundary_factor = lab->boundary_factor;
             rp.N_e = (int)lab->N_e;
             rp.n_e0 = (int)(lab->N_e * lab->e_ratio_start[k]);                        // tl_trap_lab.py:38
             rp.n_h0 = n_h0;
-            rp.protocol = lab->protocol;
+            rp.protocol = legacy ? MCL_PROTO_TL_LEGACY : lab->protocol;
             rp.seg_begin = k; rp.seg_count = 1;
             rp.obs_begin = iso ? c * n_obs + lab->obs_begin[k] : 0;
             rp.obs_count = iso ? lab->obs_begin[k + 1] - lab->obs_begin[k] : 0;
@@ -142,16 +155,17 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
     a.final_n_e = (int32_t *)d_final.p; a.esteps = (int64_t *)d_esteps.p; a.status = (int32_t *)d_status.p;
     a.obs_n_e = iso ? (int32_t *)d_obs.p : nullptr;
     a.stream = stream;
-    size_t need = mcl_workspace_bytes(&a);
-    if (!need) return MCL_ERR_ARG;
+    size_t need = 0;
+    PlannedRun *plan = mcl_plan(&a, &need);
+    if (!plan) return MCL_ERR_ARG;
     void *scratch = g_scratch.get(need);
-    if (!scratch) { set_error("mcl_objective: cudaMalloc(workspace %zu) failed", need); return MCL_ERR_ALLOC; }
+    if (!scratch) { mcl_plan_discard(plan); set_error("mcl_objective: cudaMalloc(workspace %zu) failed", need); return MCL_ERR_ALLOC; }
     a.workspace = scratch; a.workspace_bytes = need;
     // kernel time of this call (H2D of the tables excluded), for the benchmark's roofline line
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     const bool timed = cudaEventCreate(&ev0) == cudaSuccess && cudaEventCreate(&ev1) == cudaSuccess;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = mcl_run_timed(&a, timed ? (void *)ev0 : nullptr, timed ? (void *)ev1 : nullptr);
+    int rc = mcl_run_planned(&a, plan, timed ? (void *)ev0 : nullptr, timed ? (void *)ev1 : nullptr);
     if (rc) { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); return rc; }
 
     std::vector<int32_t> final_n(R), status(R), obs_n(obs.size());

@@ -118,8 +118,10 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
     // electron state of this lane's four slots
     float c[4], px[4], py[4], pz[4];
     int nh[4];
+    int birth[4];                  // creation order (legacy semantics: the OLDEST electron is the one that recombines)
 #pragma unroll
-    for (int k = 0; k < 4; k++) { c[k] = F_INF; nh[k] = -1; px[k] = py[k] = pz[k] = 0.f; }
+    for (int k = 0; k < 4; k++) { c[k] = F_INF; nh[k] = -1; px[k] = py[k] = pz[k] = 0.f; birth[k] = 4 * lane + k; }
+    int next_birth = rp.n_e0;
 
     if (status == MCL_OK) {
         // ---------------- Box.seed (engine.py:124-129): holes in generation order, electrons slot i = electron i
@@ -162,6 +164,12 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
     const float cr_far = bnd_s * 1.7320508f;
 
     const bool iso = rp.protocol == MCL_PROTO_ISO_LAB;
+    // Legacy (pre-refactor) TL semantics, reference src/est_params/functions.py:270-360: ONE channel draw per step for all
+    // electrons (:125), every cache exact again after a pair is added (:316-317), the electron that recombines is the
+    // OLDEST one whatever the waiting times say (np.where(...)[0] on a (1, n) array returns row indices, :246), and a
+    // recombination re-adds a fresh pair with probability Retrap (:328-331).
+    const bool legacy = rp.protocol == MCL_PROTO_TL_LEGACY;
+    const float retrap_f = (float)rp.Retrap;
     const double *obs = p.obs_time + rp.obs_begin;
     const float dose_over_D0 = (float)(S.dose_rate / rp.D0);
     const bool dose_on = S.dose_rate != 0.0;
@@ -186,6 +194,7 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
         // step ended at (tl_trap_lab.py:93,105); ISO_lab is isothermal
         float A1, A2, g;
         bool has_cb;
+        uint32_t leg_retrap_word = 0u;
         {
             const float T_now = (float)(iso ? T0K : (S.T_start + S.T_rate * t_cur + 273.15));
             float invT;
@@ -193,6 +202,12 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
             A1 = fmaf(-eb1, invT, lb); A2 = fmaf(-eb2, invT, lb);
             if (one_ch_2) A1 = A2;
             if (one_ch_1) A2 = A1;
+            if (legacy) {            // all electrons share the channel of this step: `rand(1) > Retrap` -> E_loc_1
+                uint32_t s0 = 2u, s1 = (uint32_t)rec_i, s2 = rid_lo, s3 = rid_hi | (DOM_SCALAR << 28);
+                philox4x32_10(s0, s1, s2, s3, K);
+                leg_retrap_word = s1;
+                A1 = A2 = (u01(s0) > retrap_f) ? A1 : A2;
+            }
             g = fmaf(-ecb, invT, ls);
             has_cb = g > fminf(A1, A2) - cr_far - 30.0f;
         }
@@ -248,11 +263,55 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
         esteps += n_e;
         t_cur += (double)dt;
 
+        // Adds one electron + its twin hole.  Current semantics (Box.add_electron, engine.py:133-152): the new electron sees the
+        // OLD holes only and nobody sees the new hole.  `exact` (legacy): afterwards every cache is exact, twin included.
+        auto add_pair = [&](float nx, float ny, float nz, float qx, float qy, float qz, bool exact) -> bool {
+            float d2; int j, hs;
+            sb_search<true>(hx, hy, hz, n_hs, nx, ny, nz, lane, d2, j, hs);
+            if (j < 0 && !exact) { status = MCL_ERR_NOHOLES; return false; }
+            uint32_t fm = 0u;                                   // lowest free electron slot
+#pragma unroll
+            for (int k = 0; k < 4; k++) fm |= !(c[k] < F_INF) ? (1u << k) : 0u;
+            const int es = (int)warp_min_u32(fm ? (uint32_t)(4 * lane + __ffs(fm) - 1) : 0x7fffffffu);
+            if (es >= 124 || hs >= hcap) { status = MCL_ERR_CAPACITY; return false; }
+            float cnew = sqrtf(d2);
+            int jn = j;
+            if (exact) {
+                const float tx = nx - qx, ty = ny - qy, tz = nz - qz;
+                const float dt2 = fmaf(tx, tx, fmaf(ty, ty, tz * tz));
+                if (j < 0 || dt2 < d2) { cnew = sqrtf(dt2); jn = hs; }       // np.argmin keeps the older hole on an exact tie
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float ex_ = px[k] - qx, ey_ = py[k] - qy, ez_ = pz[k] - qz;
+                    const float dd = sqrtf(fmaf(ex_, ex_, fmaf(ey_, ey_, ez_ * ez_)));
+                    if (c[k] < F_INF && dd < c[k]) { c[k] = dd; nh[k] = hs; }
+                }
+            }
+            if (lane == (es >> 2)) {
+                const int k = es & 3;
+                set4(c, k, cnew); set4(nh, k, jn); set4(px, k, nx); set4(py, k, ny); set4(pz, k, nz); set4(birth, k, next_birth);
+            }
+            if (lane == 0) { hx[hs] = qx; hy[hs] = qy; hz[hs] = qz; }
+            next_birth++;
+            n_slots = max(n_slots, es + 1);
+            n_hs = max(n_hs, hs + 1);
+            n_e++;
+            __syncwarp();
+            return true;
+        };
+
         int ev = 0;
         if (!is_fill) {
-            // ---------------- Box.remove_pair (engine.py:154-175)
+            // ---------------- Box.remove_pair (engine.py:154-175) / legacy recomber (functions.py:241-261)
             ev = 1;
-            const int own = smin >> 2, ks = smin & 3;
+            int victim = smin;
+            if (legacy) {                    // the oldest alive electron
+                uint32_t key = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (c[k] < F_INF) key = min(key, ((uint32_t)birth[k] << 7) | (uint32_t)(4 * lane + k));
+                victim = (int)(warp_min_u32(key) & 127u);
+            }
+            const int own = victim >> 2, ks = victim & 3;
             const int hsel = pick4(nh[0], nh[1], nh[2], nh[3], ks);
             const int h = __shfl_sync(0xffffffffu, hsel, own);
             if (lane == own) { set4(c, ks, F_INF); set4(nh, ks, -1); }
@@ -260,9 +319,10 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
             if (lane == 0) hx[h] = DEAD_X;
             __syncwarp();
             // stale-cache mode: electrons cached on the hole that FOLLOWS the removed one in index order are refreshed too
-            // (shift-then-mask, engine.py:168-171); without fills every cache is exact and the refresh finds the same hole
+            // (shift-then-mask, engine.py:168-171); without fills every cache is exact and the refresh finds the same hole.
+            // The legacy code selects the electrons to refresh before it shifts: no such quirk there.
             int h2 = -1;
-            if (ever_filled) {
+            if (ever_filled && !legacy) {
                 for (int base = h + 1; base < n_hs && h2 < 0; base += 32) {
                     const int j = base + lane;
                     const unsigned m = __ballot_sync(0xffffffffu, j < n_hs && hx[j] < 0.5f * DEAD_X);
@@ -287,30 +347,23 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
                 need = __ballot_sync(0xffffffffu, hits != 0u);
             }
             if (status != MCL_OK) break;
+            if (legacy && u01(leg_retrap_word) < retrap_f) {
+                // re-trapping (functions.py:328-331): a fresh pair, positions from two more scalar calls of this step
+                uint32_t a0 = 3u, a1 = (uint32_t)rec_i, a2 = rid_lo, a3 = rid_hi | (DOM_SCALAR << 28);
+                philox4x32_10(a0, a1, a2, a3, K);
+                uint32_t b0 = 4u, b1 = (uint32_t)rec_i, b2 = rid_lo, b3 = rid_hi | (DOM_SCALAR << 28);
+                philox4x32_10(b0, b1, b2, b3, K);
+                if (!add_pair(u01(a0) * core_s, u01(a1) * core_s, u01(a2) * core_s, u01(b0) * bnd_s, u01(b1) * bnd_s, u01(b2) * bnd_s, true)) break;
+            }
         } else {
-            // ---------------- Box.add_electron (engine.py:133-152): the new electron sees the OLD holes only
+            // ---------------- Box.add_electron (engine.py:133-152) / legacy add_electron + full refresh (functions.py:214-228,316-317)
             ever_filled = true;
             const int src = rec_i & 31;
             const float nx = u01(__shfl_sync(0xffffffffu, sd1, src)) * core_s, ny = u01(__shfl_sync(0xffffffffu, sd2, src)) * core_s,
                         nz = u01(__shfl_sync(0xffffffffu, sd3, src)) * core_s;
             uint32_t d0 = 1u, d1 = (uint32_t)rec_i, d2w = rid_lo, d3 = rid_hi | (DOM_SCALAR << 28);
             philox4x32_10(d0, d1, d2w, d3, K);
-            const float qx = u01(d0) * bnd_s, qy = u01(d1) * bnd_s, qz = u01(d2w) * bnd_s;
-            float d2; int j, hs;
-            sb_search<true>(hx, hy, hz, n_hs, nx, ny, nz, lane, d2, j, hs);
-            if (j < 0) { status = MCL_ERR_NOHOLES; break; }
-            // lowest free electron slot
-            uint32_t fm = 0u;
-#pragma unroll
-            for (int k = 0; k < 4; k++) fm |= !(c[k] < F_INF) ? (1u << k) : 0u;
-            const int es = (int)warp_min_u32(fm ? (uint32_t)(4 * lane + __ffs(fm) - 1) : 0x7fffffffu);
-            if (es >= 124 || hs >= hcap) { status = MCL_ERR_CAPACITY; break; }
-            if (lane == (es >> 2)) { const int k = es & 3; set4(c, k, sqrtf(d2)); set4(nh, k, j); set4(px, k, nx); set4(py, k, ny); set4(pz, k, nz); }
-            if (lane == 0) { hx[hs] = qx; hy[hs] = qy; hz[hs] = qz; }
-            n_slots = max(n_slots, es + 1);
-            n_hs = max(n_hs, hs + 1);
-            n_e++;
-            __syncwarp();
+            if (!add_pair(nx, ny, nz, u01(d0) * bnd_s, u01(d1) * bnd_s, u01(d2w) * bnd_s, legacy)) break;
         }
         // ---------------- record (tl_trap_lab.py:107-108) and ISO observations (:153-172)
         if (TRACE && lane == 0) {
@@ -326,7 +379,7 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
             }
         }
     }
-    if (status == MCL_OK && rp.protocol == MCL_PROTO_TL_LAB && rec_i == 0) status = MCL_ERR_NOEVENT;
+    if (status == MCL_OK && rp.protocol == MCL_PROTO_TL_LAB && rec_i == 0) status = MCL_ERR_NOEVENT;     // (the legacy loop returns its start value)
     if (lane == 0) {
         if (p.steps_used) p.steps_used[r] = rec_i;
         if (p.final_n_e) p.final_n_e[r] = n_e;
@@ -341,7 +394,7 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
 // Per-replica eligibility (never a property of the launch): lab protocol, at most 124 traps, holes that fit shared memory.
 bool smallbox_eligible(const mcl_replica &rp)
 {
-    if (rp.protocol != MCL_PROTO_TL_LAB && rp.protocol != MCL_PROTO_ISO_LAB) return false;
+    if (rp.protocol != MCL_PROTO_TL_LAB && rp.protocol != MCL_PROTO_ISO_LAB && rp.protocol != MCL_PROTO_TL_LEGACY) return false;
     if (rp.N_e > 124 || rp.n_e0 > 124 || rp.N_e < 0) return false;
     return smallbox_hole_capacity(rp) <= kSmallboxMaxHoles;
 }

@@ -72,7 +72,7 @@ def objective(p: np.ndarray, cfg: Mapping[str, Any], exp: str, **kw) -> float:
 
 
 def objective_batched(P: np.ndarray, cfg: Mapping[str, Any], exp: str, *, seed=None,
-                      candidate_id0: int = 0, return_esteps: bool = False):
+                      candidate_id0: int = 0, return_esteps: bool = False, legacy: bool = False):
     """``objective`` for a whole population: ``P[10, S]`` -> ``mse[S]``, one GPU launch.
 
     This is the seam SciPy offers with ``differential_evolution(..., vectorized=True,
@@ -115,6 +115,7 @@ def objective_batched(P: np.ndarray, cfg: Mapping[str, Any], exp: str, *, seed=N
     lab.N_e, lab.boundary_factor = float(mc["N_e"]), float(mc["boundary_factor"])
     lab.D, lab.k_b = float(phys["D"] if phys["D"] is not None else 0.0), float(phys["k_b"])
     lab.max_steps = int(mc["steps"])
+    lab.flags = 1 if (legacy or cfg.get("legacy", False)) else 0       # MCL_LAB_LEGACY: pre-refactor est_params semantics (TL only)
     if seed is None:
         seed = cfg.get("seed", None)
     if seed is None:

@@ -36,7 +36,8 @@ def lab_table(csv_name: str, protocol: int, root: Optional[str] = None) -> LabTa
 
 class TLTrapSim:
     def __init__(self, cfg: Mapping[str, Any], *, e_ratio_start: Optional[float] = None,
-                 rng: Optional[str] = None, seed: Optional[int] = None, candidate_id: int = 0, device=None):
+                 rng: Optional[str] = None, seed: Optional[int] = None, candidate_id: int = 0, device=None,
+                 legacy: Optional[bool] = None):
         self.cfg = cfg
         self.mc = cfg["exp_type_fp"]
         self.phys = SimpleNamespace(**physics_record(cfg["physics_fp"]))   # TypeError like Physics(**...)
@@ -47,6 +48,11 @@ class TLTrapSim:
         self.seed = seed if seed is not None else cfg.get("seed", None)
         self.device = device
         self.candidate_id = int(candidate_id)     # global id of this parameter set (Philox stream key)
+        # legacy=True: TL_lab follows the PRE-REFACTOR code (reference src/est_params/functions.py:270-360, what produced
+        # results/lab_sims/result_*.csv) instead of src/class/tl_trap_lab.py -- see MCL_PROTO_TL_LEGACY in mcl_b200.h
+        self.legacy = bool(legacy if legacy is not None else cfg.get("legacy", False))
+        if self.legacy and self.rng == "replay":
+            raise ValueError("the legacy semantics run in native (philox) mode only")
         self.last_esteps = 0
         if self.rng == "replay":
             # the reference constructor seeds a Box: 3*(e0 + n_h0) uniforms leave the global stream
@@ -56,7 +62,7 @@ class TLTrapSim:
 
     # ------------------------------------------------------------------
     def _run(self, lt: LabTable):
-        reps, segs = lt.tables(self.cfg)
+        reps, segs = lt.tables(self.cfg, legacy=self.legacy)
         steps = int(self.mc["steps"])
         if self.rng == "replay":
             res = engine.run_replay_chained(reps, segs, steps, engine.global_replay(),

@@ -90,3 +90,44 @@ def test_kernel_temperature_histogram_gives_the_reference_glow_curve(gpu):
         assert m >= 700
         assert np.allclose(got[:m], want[:m], rtol=0, atol=1e-12), (r, np.abs(got[:m] - want[:m]).max())
         assert want[:m].max() > 0
+
+
+def test_legacy_est_params_semantics_on_the_gpu(gpu, capsys):
+    """the pre-refactor TL code (reference src/est_params/functions.py:270-360), selectable with
+    `legacy=True`.  GPU (native Philox) against the oracle's legacy mode, which is pinned bit-for-bit against the
+    unmodified legacy function (tests/test_oracle_golden.py); batched == single; and the reference's recorded optimum
+    (results/lab_sims/result_tl_clbr.csv, first row) scores a few 1e-3 under its own semantics but ~0.02 under the
+    current ones."""
+    from mcluminescence_b200 import engine, optimizer
+    from mcluminescence_b200.config import compose
+    from oracle import mcl_oracle as mo
+    golden = helpers.Golden()
+    cfg = compose(overrides=helpers.LAB_OVERRIDES)
+    for name in ("legacy_default", "legacy_best_row", "legacy_sobol2"):
+        meta = golden.meta(name)
+        lt, reps1, segs, run = helpers.legacy_setup(meta)
+        assert np.all(reps1["protocol"] == 3)
+        M, n_rows, steps = 96, len(reps1), int(run["exp_type_fp"]["steps"])
+        reps = np.tile(reps1, M)
+        out = engine.run_replicas(reps, segs, steps, seed=700, trace=False, sync=True)
+        out.raise_on_error()
+        ref = mo.run(reps, segs, steps, seed=800, parallel=True, trace=False)
+        assert ref.rc == 0
+        g, o = out.final_n_e.reshape(M, n_rows).astype(float), ref.final_n_e.reshape(M, n_rows).astype(float)
+        for k in range(n_rows):
+            se = np.sqrt(g[:, k].var(ddof=1) / M + o[:, k].var(ddof=1) / M)
+            assert abs(g[:, k].mean() - o[:, k].mean()) <= 4.0 * se + 0.3, (name, k, g[:, k].mean(), o[:, k].mean(), se)
+        ge, oe = out.esteps.reshape(M, n_rows).sum(1).astype(float), ref.esteps.reshape(M, n_rows).sum(1).astype(float)
+        se = np.sqrt(ge.var(ddof=1) / M + oe.var(ddof=1) / M)
+        assert abs(ge.mean() - oe.mean()) <= 4.0 * se, (name, ge.mean(), oe.mean(), se)
+    # the Optimizer seam: batched == single candidate, legacy != current
+    best = np.asarray(golden.meta("legacy_best_row")["p"])
+    P = np.tile(best[:, None], (1, 64))
+    leg = optimizer.objective_batched(P, cfg, "tl_clbr", seed=9, legacy=True)
+    cur = optimizer.objective_batched(P, cfg, "tl_clbr", seed=9)
+    one = optimizer.objective(best, cfg, "tl_clbr", seed=9, candidate_id=5, legacy=True)
+    assert one == leg[5]
+    assert leg.mean() < 0.008 and leg.min() < 0.004 and cur.mean() > 2.0 * leg.mean(), (leg.mean(), leg.min(), cur.mean())
+    with pytest.raises(Exception):
+        optimizer.objective_batched(P, cfg, "iso", seed=9, legacy=True)
+    capsys.readouterr()
