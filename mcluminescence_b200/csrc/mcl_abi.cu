@@ -31,7 +31,12 @@ struct Layout {
     // queue and the long replicas do not end up in the tail of the launch.
     std::vector<int32_t> small, big;
     int small_hcap;
+    // the small list is launched in hole-capacity classes (shared memory per warp = 12 bytes x class capacity, so the
+    // small boxes of a population are not held to the occupancy of its largest one): [begin, end) into `small` + capacity
+    struct SmallClass { int begin, end, hcap; };
+    std::vector<SmallClass> small_classes;
 };
+static const int kSmallClassCaps[] = {384, 640, 896, 1152, 1536, 2048, 3072, kSmallboxMaxHoles};
 
 // expected work of a replica, up to a constant: what the launch order sorts by
 static double work_estimate(const mcl_run_args *a, const mcl_replica &rp)
@@ -127,8 +132,26 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
             size_t o2 = 0;
             for (auto &b : bucket) for (int32_t r : b) list[o2++] = r;
         };
-        order_list(L->small);
         order_list(L->big);
+        // small boxes: by capacity class first, longest work first inside a class
+        L->small_classes.clear();
+        std::vector<int32_t> all_small;
+        all_small.swap(L->small);
+        for (int cap : kSmallClassCaps) {
+            std::vector<int32_t> cls;
+            int hmax = 0;
+            for (int32_t r : all_small) {
+                const int hc = smallbox_hole_capacity(a->replicas[r]);
+                bool mine = hc <= cap;
+                for (int c2 : kSmallClassCaps) { if (c2 >= cap) break; if (hc <= c2) { mine = false; break; } }
+                if (mine) { cls.push_back(r); hmax = std::max(hmax, hc); }
+            }
+            if (cls.empty()) continue;
+            order_list(cls);
+            const int b = (int)L->small.size();
+            L->small.insert(L->small.end(), cls.begin(), cls.end());
+            L->small_classes.push_back(Layout::SmallClass{b, (int)L->small.size(), hmax});
+        }
     }
     L->total = o;
     return MCL_OK;
@@ -196,7 +219,8 @@ static int run_device(const mcl_run_args *a, cudaEvent_t ev0 = nullptr, cudaEven
     cudaError_t e = cudaSuccess;
     if (a->mode == MCL_MODE_REPLAY) e = launch_replay(p, st);
     else {
-        if (!L.small.empty()) e = launch_smallbox(p, order_dev, (int)L.small.size(), L.small_hcap, st);
+        for (const auto &c : L.small_classes)
+            if (e == cudaSuccess) e = launch_smallbox(p, order_dev + c.begin, c.end - c.begin, c.hcap, st);
         if (e == cudaSuccess && !L.big.empty()) e = launch_philox(p, st, 0);
     }
     if (ev1) cudaEventRecord(ev1, st);

@@ -54,6 +54,24 @@ namespace {
 #ifndef MCL_ONE_CHAINS
 #define MCL_ONE_CHAINS 2
 #endif
+#ifndef MCL_OLD_TIEBREAK
+#define MCL_OLD_TIEBREAK 0      // tuning toggle: 1 = ties by lane order (depends on the CTA width)
+#endif
+// Resident CTAs per SM the narrow kernels are compiled for (= their register cap).  Measured on B200 (C5, 2000-electron boxes,
+// 64 threads): 8 CTAs at 128 registers beat 16 CTAs at 64 registers by 9 % -- the spills of the 64-register build sit in
+// the serial part of every step.  The 256-thread kernel (C2) is the other way round: 3 CTAs at 80 registers beat 2 at 128.
+#ifndef MCL_NT64_MINB
+#define MCL_NT64_MINB 8
+#endif
+#ifndef MCL_NT128_MINB
+#define MCL_NT128_MINB 4
+#endif
+#ifndef MCL_NT32_MINB
+#define MCL_NT32_MINB 16
+#endif
+#ifndef MCL_NT256_MINB
+#define MCL_NT256_MINB 3
+#endif
 constexpr float F_INF = __builtin_huge_valf();
 constexpr float DEAD_X = 1e30f;
 constexpr float LN2F = 0.69314718055994530942f;
@@ -85,11 +103,13 @@ struct Cfg {
 };
 
 
-// Rare path of the channel selector (a 9-bit tie, probability 2^-9 per electron-step): the four words that settle the
-// ties of one chunk.  Out of line, with the round keys rebuilt from the two key words, so that the sweep carries
-// neither its code nor its registers.
-__device__ __noinline__ bool philox_tie_is_ch2(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                                               int k, uint32_t sel_frac)
+// Rare path of the channel selector (a 9-bit tie, probability 2^-9 per electron-step, and only for slots within reach of
+// the running minimum): settles the flagged slots of up to two chunks with one more Philox word each and returns the
+// improved (clock, slot) minimum.  Completely out of line -- it regenerates the chunk's words, re-reads its distances and
+// rebuilds the round keys from the two key words -- so that the sweep carries neither its code nor its registers: only
+// (best, bslot) cross the call.  Equal clocks go to the smaller slot, as everywhere.
+struct TieFix { float best; int bslot; };
+__device__ __noinline__ uint4 philox_rolled(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
 #pragma unroll 1
     for (int r = 0; r < 10; r++) {
@@ -100,10 +120,39 @@ __device__ __noinline__ bool philox_tie_is_ch2(uint32_t c0, uint32_t c1, uint32_
         c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
         k0 += PHILOX_W0; k1 += PHILOX_W1;
     }
-    const uint32_t w = k == 0 ? c0 : (k == 1 ? c1 : (k == 2 ? c2 : c3));
-    return w < sel_frac;
+    return make_uint4(c0, c1, c2, c3);
 }
-
+__device__ __noinline__ TieFix philox_settle_ties(uint32_t tmask, int b0, int nt, uint32_t rec_i, uint32_t rid_lo, uint32_t rid_hi,
+                                                  uint32_t k0, uint32_t k1, const float *cr, float A_fast, float g, int with_cb,
+                                                  uint32_t sel_frac, int ch2_fast, float best, int bslot)
+{
+#pragma unroll 1
+    for (int q = 0; q < 2; q++, tmask >>= 4) {
+        if (!(tmask & 0xfu)) continue;
+        const int b = b0 + q * nt;
+        const uint4 wv = philox_rolled((uint32_t)b, rec_i, rid_lo, rid_hi | (DOM_STEP1 << 28), k0, k1);
+        const uint4 tv = philox_rolled((uint32_t)b, rec_i, rid_lo, rid_hi | (DOM_SEL << 28), k0, k1);
+        const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w}, t[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!((tmask >> k) & 1u)) continue;
+            if ((t[k] < sel_frac) != (ch2_fast != 0)) continue;          // the tie goes to the slower channel: nothing to gain
+            const float c = cr[4 * b + k];
+            const float le = lg2_fast(-lg2_fast(u01(w[k])));
+            float l2;
+            if (with_cb) {
+                const float a = A_fast - c;
+                const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
+                l2 = (le - kk) + (c - c);
+            } else {
+                l2 = (le + c) - A_fast;
+            }
+            const int sl2 = 4 * b + k;
+            if (l2 < best || (l2 == best && sl2 < bslot)) { best = l2; bslot = sl2; }
+        }
+    }
+    return TieFix{best, bslot};
+}
 
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 {
@@ -603,6 +652,10 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     // P(channel 2) = T9/512 + frac/512 = Retrap, exact to 2^-41.  Retrap >= 1 / <= 0 collapse the two channels.
     const bool one_ch_2 = rp.Retrap >= 1.0, one_ch_1 = rp.Retrap <= 0.0;
     const double sel_scaled = (one_ch_1 || one_ch_2) ? 0.0 : rp.Retrap * 512.0;
+    // (the selector constants live in shared memory and are fetched by the two-channel sweep only: the identical-channel
+    // sweep of the BASELINE ensembles should not carry their registers through the step loop)
+    __shared__ uint32_t s_sel[4];              // sel_cmp, sel_tie, sel_frac, ch2_fast
+    if (tid == 0) {
     const uint32_t sel_T9 = (uint32_t)sel_scaled;
     const uint32_t sel_frac = (uint32_t)fmin((sel_scaled - (double)sel_T9) * 4294967296.0, 4294967295.0);
     const uint32_t sel_tie = sel_frac ? sel_T9 : 0xffffu;           // no remainder: sel9 == T9 is plain channel 1
@@ -610,6 +663,8 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     // settles the ties that could still win the step with the faster one.  Which channel is faster does not depend on T.
     const bool ch2_fast = rp.E_loc_2 <= rp.E_loc_1;
     const uint32_t sel_cmp = (sel_frac && !ch2_fast) ? sel_T9 + 1u : sel_T9;
+    s_sel[0] = sel_cmp; s_sel[1] = sel_tie; s_sel[2] = sel_frac; s_sel[3] = ch2_fast ? 1u : 0u;
+    }       // (published by the barriers of the seeding phase / the first step barrier's predecessor below)
     const float cr_far = bnd_s * 1.7320508f;        // no electron-hole distance exceeds the box diagonal
 
     const bool lab = rp.protocol != MCL_PROTO_SIMULATE;
@@ -845,10 +900,11 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 // A thread owns whole CHUNKS of SPC = 4 slots (chunk b = slots 4b.. belongs to thread b % NT): one 16-byte
                 // load feeds the clocks of a chunk and the post-event scan reads its nearest-hole slots with one load.
                 const int n_chunks = (n_slots + SPC - 1) / SPC;
-                const float A_fast = fmaxf(A1, A2), dA_ch = A_fast - fminf(A1, A2);
                 auto pair_loop = [&](auto with_cb, auto one_channel) {
                     constexpr bool CB = decltype(with_cb)::value;
                     constexpr bool ONE = decltype(one_channel)::value;     // both tunnelling channels identical
+                    const float A_fast = fmaxf(A1, A2), dA_ch = A_fast - fminf(A1, A2);
+                    const uint32_t sel_cmp = ONE ? 0u : s_sel[0], sel_tie = ONE ? 0u : s_sel[1];
                     // One Philox call serves the FOUR slots of a chunk (word k -> slot 4b + k): the top 23 bits of a word are
                     // the electron's exponential draw, its 9 low bits the channel selector (not looked at when the channels
                     // are identical).  MCL_ONE_CHAINS chunks of the same owner per iteration keep that many independent
@@ -891,23 +947,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                             }
                         }
                         if (!ONE && __builtin_expect(tmask != 0u, 0)) {
-                            // rare (2^-9 per slot, and only slots within reach of the running minimum): settle the tie with one more
-                            // word; if it picks the faster channel the clock improves.  Equal clocks go to the smaller slot, as everywhere.
-#pragma unroll
-                            for (int q = 0; q < NCH; q++) {
-#pragma unroll
-                                for (int k = 0; k < 4; k++) {
-                                    if ((tmask >> (4 * q + k)) & 1u) {
-                                        const bool is2 = philox_tie_is_ch2((uint32_t)(b0 + q * NT), (uint32_t)rec_i, rid_lo, rid_hi | (DOM_SEL << 28), K.k[0], K.k[1], k, sel_frac);
-                                        if (is2 == ch2_fast) {
-                                            const float le = lg2_fast(-lg2_fast(u01(w[q][k])));
-                                            const float l2 = CB ? clock_cb(le, cs[q][k], A_fast) : (le + cs[q][k]) - A_fast;
-                                            const int sl2 = 4 * (b0 + q * NT) + k;
-                                            if (l2 < best || (l2 == best && sl2 < bslot)) { best = l2; bslot = sl2; }
-                                        }
-                                    }
-                                }
-                            }
+                            const TieFix f = philox_settle_ties(tmask, b0, NT, (uint32_t)rec_i, rid_lo, rid_hi, K.k[0], K.k[1], cr, A_fast, g,
+                                                                CB ? 1 : 0, s_sel[2], (int)s_sel[3], best, bslot);
+                            best = f.best; bslot = f.bslot;
                         }
                     };
                     int b0 = tid;
@@ -925,8 +967,12 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     float wv = warp_min_f32(best);
                     const unsigned m = __ballot_sync(0xffffffffu, best == wv);
                     int ws_;
+#if MCL_OLD_TIEBREAK
+                    ws_ = __shfl_sync(0xffffffffu, bslot, m ? (__ffs(m) - 1) : 0);
+#else
                     if (m & (m - 1u)) ws_ = (int)warp_min_u32(best == wv ? (uint32_t)bslot : 0xffffffffu);   // tie (2^-18 per step), or no clock at all: -1
                     else ws_ = __shfl_sync(0xffffffffu, bslot, m ? (__ffs(m) - 1) : 0);
+#endif
                     __syncwarp();
                     if (lane == 0) red_row[par][warp] = make_int4(__float_as_int(wv), ws_, ws_ >= 0 ? (int)near[ws_] : -1, 0);
                 }
@@ -955,7 +1001,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     const int s = row.y, hh = row.z;
                     vmin = warp_min_f32(v);
                     unsigned m = __ballot_sync(0xffffffffu, v == vmin);
-                    if (m & (m - 1u)) {             // tied rows (or no clock anywhere): the smallest slot wins, whatever warp holds it
+                    if (!MCL_OLD_TIEBREAK && (m & (m - 1u))) {             // tied rows (or no clock anywhere): the smallest slot wins, whatever warp holds it
                         const int s_low = (int)warp_min_u32(v == vmin ? (uint32_t)s : 0xffffffffu);
                         m = __ballot_sync(0xffffffffu, v == vmin && s == s_low);
                     }
@@ -1464,18 +1510,22 @@ cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_
     case NT_:                                                                                      \
         return pl.near16 ? launch_one<NT_, MINB_, uint16_t, PPC_>(p, K, cfg, pl.smem, stream)      \
                          : launch_one<NT_, MINB_, uint32_t, PPC_>(p, K, cfg, pl.smem, stream)
+#ifdef MCL_ONLY_C2          // build-time probe (scripts/regs_probe.sh): only the BASELINE C2 instantiation, for quick ptxas -v runs
+    return launch_two<256, MCL_NT256_MINB, uint16_t, 2, false, false>(p, K, cfg, pl.smem, stream);
+#else
     if (pl.slab_smem)       // (implies nt == 32) few CTAs per SM: no register cap worth the name
         return pl.near16 ? launch_one<32, 12, uint16_t, 2, true>(p, K, cfg, pl.smem, stream)
                          : launch_one<32, 12, uint32_t, 2, true>(p, K, cfg, pl.smem, stream);
     switch (pl.nt) {
-        MCL_CASE(32, 32, 2);
-        MCL_CASE(64, 16, 2);
-        MCL_CASE(128, 8, 2);
-        MCL_CASE(256, 3, 2);
+        MCL_CASE(32, MCL_NT32_MINB, 2);
+        MCL_CASE(64, MCL_NT64_MINB, 2);
+        MCL_CASE(128, MCL_NT128_MINB, 2);
+        MCL_CASE(256, MCL_NT256_MINB, 2);
         default: break;
     }
     return pl.near16 ? launch_one<512, 2, uint16_t, 2>(p, K, cfg, pl.smem, stream)
                      : launch_one<512, 2, uint32_t, 2>(p, K, cfg, pl.smem, stream);
+#endif
 #undef MCL_CASE
 }
 

@@ -8,7 +8,7 @@ lib=$root/mcluminescence_b200/_lib; src=$root/mcluminescence_b200/csrc
 mkdir -p $root/scripts/ab_libs
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --extended-lambda -Xcompiler -fPIC \
      -I $root/include -I $src "$@" -Xptxas -v -c $src/mcl_philox.cu -o /tmp/mcl_philox_$name.o 2> /tmp/mcl_philox_$name.log
-grep -A2 "philox_kernelILi256ELi3Et" /tmp/mcl_philox_$name.log | grep -E "spill|registers" | tr '\n' ' '; echo
+grep -A2 "philox_kernelILi256ELi[0-9]*EtLi2ELb0ELb0E\|philox_kernelILi64ELi[0-9]*EtLi2ELb0ELb0E" /tmp/mcl_philox_$name.log | grep -E "spill|registers" | tr '\n' ' '; echo
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $root/scripts/ab_libs/$name.so \
-     $lib/mcl_abi.o $lib/mcl_replay.o /tmp/mcl_philox_$name.o $lib/mcl_peaks.o $lib/mcl_objective.o
+     $lib/mcl_abi.o $lib/mcl_replay.o /tmp/mcl_philox_$name.o $lib/mcl_smallbox.o $lib/mcl_peaks.o $lib/mcl_objective.o
 echo built scripts/ab_libs/$name.so

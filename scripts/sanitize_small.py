@@ -23,4 +23,19 @@ for exp in ("tl_clbr", "iso"):
     lt = LabTable(*LAB_CSV[exp], PROJECT_ROOT)
     r, s = lt.tables(run)
     out = engine.run_replicas(r, s, 20000, seed=4, obs_time=lt.obs_time, trace=False, sync=True); out.raise_on_error()
+    if exp == "tl_clbr":                                                                     # legacy semantics (one-warp kernel)
+        r, s = lt.tables(run, legacy=True)
+        out = engine.run_replicas(r, s, 20000, seed=4, trace=True, sync=True); out.raise_on_error()
+import os
+os.environ["MCL_SMALLBOX"] = "0"                                                            # the same rows on the block kernel: fills,
+os.environ["MCL_PHILOX_FILL_EXTRA"] = "-92"                                                 # regrids, shared-memory slab
+for exp in ("tl_clbr", "iso"):
+    lt = LabTable(*LAB_CSV[exp], PROJECT_ROOT)
+    r, s = lt.tables(run)
+    out = engine.run_replicas(r, s, 20000, seed=4, obs_time=lt.obs_time, trace=False, sync=True); out.raise_on_error()
+del os.environ["MCL_SMALLBOX"], os.environ["MCL_PHILOX_FILL_EXTRA"]
+wl = workloads.c3(replicas_per_dose=1)                                                      # dose -> TL on one box: regrid + list rebuild
+wl["replicas"]["N_e"] = 300
+out = engine.run_replicas(wl["replicas"][:3], wl["segments"], wl["max_steps"], seed=5, hist=wl["hist"], hist_group=wl["hist_group"][:3],
+                          trace=False, sync=True); out.raise_on_error()
 print("sanitize_small ok", int(out.esteps.sum()))
