@@ -103,57 +103,6 @@ struct Cfg {
 };
 
 
-// Rare path of the channel selector (a 9-bit tie, probability 2^-9 per electron-step, and only for slots within reach of
-// the running minimum): settles the flagged slots of up to two chunks with one more Philox word each and returns the
-// improved (clock, slot) minimum.  Completely out of line -- it regenerates the chunk's words, re-reads its distances and
-// rebuilds the round keys from the two key words -- so that the sweep carries neither its code nor its registers: only
-// (best, bslot) cross the call.  Equal clocks go to the smaller slot, as everywhere.
-struct TieFix { float best; int bslot; };
-__device__ __noinline__ uint4 philox_rolled(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
-{
-#pragma unroll 1
-    for (int r = 0; r < 10; r++) {
-        unsigned long long p0 = (unsigned long long)PHILOX_M0 * c0;
-        unsigned long long p1 = (unsigned long long)PHILOX_M1 * c2;
-        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
-        k0 += PHILOX_W0; k1 += PHILOX_W1;
-    }
-    return make_uint4(c0, c1, c2, c3);
-}
-__device__ __noinline__ TieFix philox_settle_ties(uint32_t tmask, int b0, int nt, uint32_t rec_i, uint32_t rid_lo, uint32_t rid_hi,
-                                                  uint32_t k0, uint32_t k1, const float *cr, float A_fast, float g, int with_cb,
-                                                  uint32_t sel_frac, int ch2_fast, float best, int bslot)
-{
-#pragma unroll 1
-    for (int q = 0; q < 2; q++, tmask >>= 4) {
-        if (!(tmask & 0xfu)) continue;
-        const int b = b0 + q * nt;
-        const uint4 wv = philox_rolled((uint32_t)b, rec_i, rid_lo, rid_hi | (DOM_STEP1 << 28), k0, k1);
-        const uint4 tv = philox_rolled((uint32_t)b, rec_i, rid_lo, rid_hi | (DOM_SEL << 28), k0, k1);
-        const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w}, t[4] = {tv.x, tv.y, tv.z, tv.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (!((tmask >> k) & 1u)) continue;
-            if ((t[k] < sel_frac) != (ch2_fast != 0)) continue;          // the tie goes to the slower channel: nothing to gain
-            const float c = cr[4 * b + k];
-            const float le = lg2_fast(-lg2_fast(u01(w[k])));
-            float l2;
-            if (with_cb) {
-                const float a = A_fast - c;
-                const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
-                l2 = (le - kk) + (c - c);
-            } else {
-                l2 = (le + c) - A_fast;
-            }
-            const int sl2 = 4 * b + k;
-            if (l2 < best || (l2 == best && sl2 < bslot)) { best = l2; bslot = sl2; }
-        }
-    }
-    return TieFix{best, bslot};
-}
-
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 {
 #pragma unroll
@@ -444,7 +393,10 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     constexpr uint32_t NEAR_DEAD = NearTraits<NearT>::DEAD;
     constexpr int SPC = 2 * PPC;              // slots per chunk: a thread owns whole chunks (chunk b -> thread b % NT)
     static_assert(PPC == 2, "a chunk is four slots: one 16-byte load of cr[], one Philox call when the channels are identical");
-    const int r = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;      // block b runs replica order[b] in slab b
+    // block b runs replica order[b] in slab b.  The index is re-read where it is needed (start, record flushes, end)
+    // instead of being carried through the step loop in a register.
+    auto replica_index = [&]() { return p.order ? p.order[blockIdx.x] : (int)blockIdx.x; };
+    const int r = replica_index();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const mcl_replica rp = p.replicas[r];
     const unsigned long long rid = p.replica_id0 + (unsigned long long)r;
@@ -646,25 +598,13 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     const float lb = (float)log2(rp.b), ls = (float)log2(rp.s);
     const float eb1 = (float)(rp.E_loc_1 * L2E / rp.k_b), eb2 = (float)(rp.E_loc_2 * L2E / rp.k_b);
     const float ecb = (float)(rp.E_cb * L2E / rp.k_b);
-    // Channel selector U < Retrap (engine.py:72), drawn from the 9 low bits the exponential draw leaves unused in every
-    // Philox word (u01 keeps the top 23): sel9 < T9 -> channel 2, sel9 > T9 -> channel 1, sel9 == T9 -> one more word
-    // against the remainder (probability 2^-9, settled by a second call for that chunk only).
-    // P(channel 2) = T9/512 + frac/512 = Retrap, exact to 2^-41.  Retrap >= 1 / <= 0 collapse the two channels.
+    // Channel selector U < Retrap (engine.py:72)  <=>  word < thr ; Retrap >= 1 / <= 0 collapse the two channels.
+    // (The one-warp kernel of the Optimizer path takes the selector from the 9 spare low bits of the word that carries the
+    // exponential draw, ties settled by one more call: one Philox call per four electrons.  Here that variant MEASURED
+    // SLOWER than a second call per chunk -- 4.17e11 vs 4.53e11 electron-steps/s on a two-channel C2: the first chunks a
+    // thread sweeps cannot yet rule a tie out, so four warp-steps in ten paid for the settling call -- profiles/README.md.)
     const bool one_ch_2 = rp.Retrap >= 1.0, one_ch_1 = rp.Retrap <= 0.0;
-    const double sel_scaled = (one_ch_1 || one_ch_2) ? 0.0 : rp.Retrap * 512.0;
-    // (the selector constants live in shared memory and are fetched by the two-channel sweep only: the identical-channel
-    // sweep of the BASELINE ensembles should not carry their registers through the step loop)
-    __shared__ uint32_t s_sel[4];              // sel_cmp, sel_tie, sel_frac, ch2_fast
-    if (tid == 0) {
-    const uint32_t sel_T9 = (uint32_t)sel_scaled;
-    const uint32_t sel_frac = (uint32_t)fmin((sel_scaled - (double)sel_T9) * 4294967296.0, 4294967295.0);
-    const uint32_t sel_tie = sel_frac ? sel_T9 : 0xffffu;           // no remainder: sel9 == T9 is plain channel 1
-    // The sweep first takes a tied selector for the SLOWER channel (a plain compare: sel9 < sel_cmp -> channel 2) and only
-    // settles the ties that could still win the step with the faster one.  Which channel is faster does not depend on T.
-    const bool ch2_fast = rp.E_loc_2 <= rp.E_loc_1;
-    const uint32_t sel_cmp = (sel_frac && !ch2_fast) ? sel_T9 + 1u : sel_T9;
-    s_sel[0] = sel_cmp; s_sel[1] = sel_tie; s_sel[2] = sel_frac; s_sel[3] = ch2_fast ? 1u : 0u;
-    }       // (published by the barriers of the seeding phase / the first step barrier's predecessor below)
+    const uint32_t thr = (one_ch_1 || one_ch_2) ? 0u : (uint32_t)fmin(rp.Retrap * 4294967296.0, 4294967295.0);
     const float cr_far = bnd_s * 1.7320508f;        // no electron-hole distance exceeds the box diagonal
 
     const bool lab = rp.protocol != MCL_PROTO_SIMULATE;
@@ -680,7 +620,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     long long esteps = 0;
     uint32_t es32 = 0u;            // electron-steps since the last carry into `esteps`
     double t_off = 0.0;
-    const size_t rec_base = (size_t)r * (size_t)p.max_steps;
+
     const bool trace = (p.event != nullptr) || (p.n_e != nullptr) || (p.t != nullptr);
     // histogram
     const int hgroup = (p.hist.n_bins > 0 && p.hist_group) ? p.hist_group[r] : 0;
@@ -692,7 +632,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         __syncwarp();
         int first = rec_i - count;
         if (lane < count) {
-            size_t q = rec_base + (size_t)(first + lane);
+            size_t q = (size_t)replica_index() * (size_t)p.max_steps + (size_t)(first + lane);
             if (p.event) p.event[q] = rec_ev[lane];
             if (p.n_e) p.n_e[q] = rec_ne[lane];
             if (p.t) p.t[q] = rec_t[lane];
@@ -903,60 +843,77 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 auto pair_loop = [&](auto with_cb, auto one_channel) {
                     constexpr bool CB = decltype(with_cb)::value;
                     constexpr bool ONE = decltype(one_channel)::value;     // both tunnelling channels identical
-                    const float A_fast = fmaxf(A1, A2), dA_ch = A_fast - fminf(A1, A2);
-                    const uint32_t sel_cmp = ONE ? 0u : s_sel[0], sel_tie = ONE ? 0u : s_sel[1];
-                    // One Philox call serves the FOUR slots of a chunk (word k -> slot 4b + k): the top 23 bits of a word are
-                    // the electron's exponential draw, its 9 low bits the channel selector (not looked at when the channels
-                    // are identical).  MCL_ONE_CHAINS chunks of the same owner per iteration keep that many independent
-                    // Philox chains in flight.
-                    const float4 *cr4 = reinterpret_cast<const float4 *>(cr);
-                    auto chunks = [&](auto n_chains, int b0) {
-                        constexpr int NCH = decltype(n_chains)::value;
-                        float cs[NCH][4];
-                        uint32_t w[NCH][4];
+                    if constexpr (ONE) {
+                        // Identical channels: the selector draw cannot change anything, so no word is spent on it.  One
+                        // Philox call serves the FOUR slots of a chunk (word k -> slot 4b + k); MCL_ONE_CHAINS chunks of
+                        // the same owner per iteration keep that many independent Philox chains in flight.
+                        const float4 *cr4 = reinterpret_cast<const float4 *>(cr);
+                        auto chunks = [&](auto n_chains, int b0) {
+                            constexpr int NCH = decltype(n_chains)::value;
+                            float cs[NCH][4];
+                            uint32_t w[NCH][4];
 #pragma unroll
-                        for (int q = 0; q < NCH; q++) {
-                            const int b = b0 + q * NT;
-                            const float4 cq = cr4[b];
-                            cs[q][0] = cq.x; cs[q][1] = cq.y; cs[q][2] = cq.z; cs[q][3] = cq.w;
-                            w[q][0] = (uint32_t)b; w[q][1] = (uint32_t)rec_i; w[q][2] = rid_lo; w[q][3] = rid_hi | (DOM_STEP1 << 28);
-                        }
-#pragma unroll
-                        for (int q = 0; q < NCH; q++) philox4x32_10(w[q][0], w[q][1], w[q][2], w[q][3], K);
-                        // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
-                        auto clock_cb = [&](float le_, float c_, float A_) {
-                            const float a = A_ - c_;
-                            const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
-                            return (le_ - kk) + (c_ - c_);
-                        };
-                        uint32_t tmask = 0u;                               // slots whose tied selector still has to be settled
-                        const float thr0 = best + dA_ch;                   // a tie on the slower channel can gain at most dA_ch
-#pragma unroll
-                        for (int q = 0; q < NCH; q++) {
-#pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                const float le = lg2_fast(-lg2_fast(u01(w[q][k])));
-                                const uint32_t sel = w[q][k] & 0x1ffu;
-                                const float Ak = ONE ? A1 : (sel < sel_cmp ? A2 : A1);
-                                float l;
-                                if (CB) l = clock_cb(le, cs[q][k], Ak);
-                                else if (ONE) l = le + cs[q][k];           // the uniform prefactor A1 is subtracted after the loop
-                                else l = (le + cs[q][k]) - Ak;
-                                if (!ONE) tmask |= (sel == sel_tie && l <= thr0) ? (1u << (4 * q + k)) : 0u;
-                                if (l < best) { best = l; bslot = 4 * (b0 + q * NT) + k; }
+                            for (int q = 0; q < NCH; q++) {
+                                const int b = b0 + q * NT;
+                                const float4 cq = cr4[b];
+                                cs[q][0] = cq.x; cs[q][1] = cq.y; cs[q][2] = cq.z; cs[q][3] = cq.w;
+                                w[q][0] = (uint32_t)b; w[q][1] = (uint32_t)rec_i; w[q][2] = rid_lo; w[q][3] = rid_hi | (DOM_STEP1 << 28);
                             }
+#pragma unroll
+                            for (int q = 0; q < NCH; q++) philox4x32_10(w[q][0], w[q][1], w[q][2], w[q][3], K);
+#pragma unroll
+                            for (int q = 0; q < NCH; q++) {
+#pragma unroll
+                                for (int k = 0; k < 4; k++) {
+                                    const float le = lg2_fast(-lg2_fast(u01(w[q][k])));
+                                    float l;
+                                    if (CB) {
+                                        // lg2(2^a + 2^g) = max + lg2(1 + 2^-|a-g|); (c - c) turns an empty slot into NaN
+                                        const float a = A1 - cs[q][k];
+                                        const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
+                                        l = (le - kk) + (cs[q][k] - cs[q][k]);
+                                    } else {
+                                        l = le + cs[q][k];              // the uniform prefactor A1 is subtracted after the loop
+                                    }
+                                    if (l < best) { best = l; bslot = 4 * (b0 + q * NT) + k; }
+                                }
+                            }
+                        };
+                        int b0 = tid;
+                        for (; b0 + (MCL_ONE_CHAINS - 1) * NT < n_chunks; b0 += MCL_ONE_CHAINS * NT)
+                            chunks(std::integral_constant<int, MCL_ONE_CHAINS>{}, b0);
+                        for (; b0 < n_chunks; b0 += NT) chunks(std::integral_constant<int, 1>{}, b0);       // tail: no wasted calls
+                        if (!CB) best -= A1;
+                    } else {
+                        // Two distinct channels: one Philox call per slot PAIR -- words 0 / 2 pick the channels, words 1 / 3 are the
+                        // exponential draws
+                        for (int b = tid; b < n_chunks; b += NT) {
+                            float cs[SPC];
+                            const float4 cq = reinterpret_cast<const float4 *>(cr)[b];
+                            cs[0] = cq.x; cs[1] = cq.y; cs[2] = cq.z; cs[3] = cq.w;
+                            float l[SPC];
+#pragma unroll
+                            for (int i = 0; i < PPC; i++) {
+                                uint32_t c0 = (uint32_t)(PPC * b + i), c1 = (uint32_t)rec_i, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);
+                                philox4x32_10(c0, c1, c2, c3, K);
+                                const float a0 = ((c0 < thr) ? A2 : A1) - cs[2 * i];
+                                const float a1 = ((c2 < thr) ? A2 : A1) - cs[2 * i + 1];
+                                const float le0 = lg2_fast(-lg2_fast(u01(c1)));
+                                const float le1 = lg2_fast(-lg2_fast(u01(c3)));
+                                if (CB) {
+                                    const float k0 = fmaxf(a0, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a0 - g)));
+                                    const float k1 = fmaxf(a1, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a1 - g)));
+                                    l[2 * i] = (le0 - k0) + (cs[2 * i] - cs[2 * i]);
+                                    l[2 * i + 1] = (le1 - k1) + (cs[2 * i + 1] - cs[2 * i + 1]);
+                                } else {
+                                    l[2 * i] = le0 - a0;
+                                    l[2 * i + 1] = le1 - a1;
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < SPC; i++) if (l[i] < best) { best = l[i]; bslot = SPC * b + i; }
                         }
-                        if (!ONE && __builtin_expect(tmask != 0u, 0)) {
-                            const TieFix f = philox_settle_ties(tmask, b0, NT, (uint32_t)rec_i, rid_lo, rid_hi, K.k[0], K.k[1], cr, A_fast, g,
-                                                                CB ? 1 : 0, s_sel[2], (int)s_sel[3], best, bslot);
-                            best = f.best; bslot = f.bslot;
-                        }
-                    };
-                    int b0 = tid;
-                    for (; b0 + (MCL_ONE_CHAINS - 1) * NT < n_chunks; b0 += MCL_ONE_CHAINS * NT)
-                        chunks(std::integral_constant<int, MCL_ONE_CHAINS>{}, b0);
-                    for (; b0 < n_chunks; b0 += NT) chunks(std::integral_constant<int, 1>{}, b0);       // tail: no wasted calls
-                    if (ONE && !CB) best -= A1;
+                    }
                 };
                 if (A1 == A2) { if (has_cb) pair_loop(std::true_type{}, std::true_type{}); else pair_loop(std::false_type{}, std::true_type{}); }
                 else          { if (has_cb) pair_loop(std::true_type{}, std::false_type{}); else pair_loop(std::false_type{}, std::false_type{}); }
@@ -1346,11 +1303,12 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     cta_sync<NT>();
     if (s_err && status == MCL_OK) status = MCL_ERR_INTERNAL;
     if (tid == 0) {
-        if (p.steps_used) p.steps_used[r] = rec_i;
-        if (p.final_n_e) p.final_n_e[r] = n_e;
-        if (p.esteps) p.esteps[r] = esteps + (long long)es32;
-        if (p.consumed) p.consumed[r] = 0;
-        if (p.status) p.status[r] = status;
+        const int r_out = replica_index();
+        if (p.steps_used) p.steps_used[r_out] = rec_i;
+        if (p.final_n_e) p.final_n_e[r_out] = n_e;
+        if (p.esteps) p.esteps[r_out] = esteps + (long long)es32;
+        if (p.consumed) p.consumed[r_out] = 0;
+        if (p.status) p.status[r_out] = status;
     }
 }
 

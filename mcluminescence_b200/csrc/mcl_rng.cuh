@@ -7,7 +7,7 @@ namespace mcl {
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 // counter domains (top 4 bits of counter word 3)
-constexpr uint32_t DOM_SCALAR = 1u, DOM_SEED_E = 2u, DOM_SEED_H = 3u, DOM_STEP1 = 4u, DOM_SEL = 5u;
+constexpr uint32_t DOM_STEP = 0u, DOM_SCALAR = 1u, DOM_SEED_E = 2u, DOM_SEED_H = 3u, DOM_STEP1 = 4u, DOM_SEL = 5u;
 
 struct RoundKeys { uint32_t k[20]; };
 
