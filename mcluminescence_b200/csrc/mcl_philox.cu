@@ -54,9 +54,6 @@ namespace {
 #ifndef MCL_ONE_CHAINS
 #define MCL_ONE_CHAINS 2
 #endif
-#ifndef MCL_DEFER_RETARGET
-#define MCL_DEFER_RETARGET 1    // 1: a re-target from the candidate lists is requested (prefetch) in the event phase and consumed
-#endif                          //    after the owner's next sweep, off the critical path of the step (same results)
 // Two clocks that are EQUAL in FP32 at the step's minimum (~2^-18 per step on a 10^4-electron box): 1 = the lowest lane, then
 // the lowest warp wins, i.e. the winner depends on which thread owns which slot and therefore on the CTA width; 0 = the
 // smallest slot wins whatever the width (exact launch-shape invariance) at a measured 2.3 % of C2's throughput (6.20e11
@@ -775,10 +772,6 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         }
         return fixed;
     };
-    // Deferred re-target (MCL_DEFER_RETARGET): the one slot of this thread whose list lookup was requested in the last event
-    // and is consumed after its next sweep; while parked its cr[] is +inf (no clock), its near[] still names the dead hole.
-    int pend = -1, pend_h = -1;
-    const bool same_channels = rp.Retrap >= 1.0 || rp.Retrap <= 0.0 || rp.E_loc_1 == rp.E_loc_2;
 
     for (int sg = 0; sg < rp.seg_count && status == MCL_OK; sg++) {
         const mcl_segment S = p.segments[rp.seg_begin + sg];
@@ -921,42 +914,6 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         for (; b0 + (MCL_ONE_CHAINS - 1) * NT < n_chunks; b0 += MCL_ONE_CHAINS * NT)
                             chunks(std::integral_constant<int, MCL_ONE_CHAINS>{}, b0);
                         for (; b0 < n_chunks; b0 += NT) chunks(std::integral_constant<int, 1>{}, b0);       // tail: no wasted calls
-#if MCL_DEFER_RETARGET
-                        if (__ballot_sync(0xffffffffu, pend >= 0)) {
-                            // a lane of this warp parked a slot in the last event: its list has arrived by now
-                            int redo2 = (pend >= 0 && !retarget_from_list(pend, pend_h)) ? pend : -1;
-                            unsigned need = __ballot_sync(0xffffffffu, redo2 >= 0);
-                            while (need) {                                  // exhausted list: the warp searches the grid
-                                const int src = __ffs(need) - 1;
-                                need &= need - 1;
-                                const int sl = __shfl_sync(0xffffffffu, redo2, src);
-                                const int hd = __shfl_sync(0xffffffffu, pend_h, src);
-                                const unsigned long long bb = warp_nearest(H, ex[sl], ey[sl], ez[sl], lane, hd);
-                                if (lane == src) {
-                                    cr[sl] = sqrtf(__uint_as_float((uint32_t)(bb >> 32))); near[sl] = (NearT)(uint32_t)bb;
-                                    if (share_bm && !ever_filled) mark_target((uint32_t)bb, sl);
-                                }
-                            }
-                            if (pend >= 0) {                                // the clock of the slot that sat this sweep out
-                                uint32_t w0 = (uint32_t)(pend >> 2), w1 = (uint32_t)rec_i, w2 = rid_lo, w3 = rid_hi | (DOM_STEP1 << 28);
-                                philox4x32_10(w0, w1, w2, w3, K);
-                                const int k = pend & 3;
-                                const uint32_t wk = k == 0 ? w0 : (k == 1 ? w1 : (k == 2 ? w2 : w3));
-                                const float c = cr[pend];
-                                const float le = lg2_fast(-lg2_fast(u01(wk)));
-                                float l;
-                                if (CB) {
-                                    const float a = A1 - c;
-                                    const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
-                                    l = (le - kk) + (c - c);
-                                } else {
-                                    l = le + c;
-                                }
-                                if (l < best || (l == best && pend < bslot)) { best = l; bslot = pend; }
-                                pend = -1;
-                            }
-                        }
-#endif
                         if (!CB) best -= A1;
                     } else {
                         // Two distinct channels: one Philox call per slot PAIR -- words 0 / 2 pick the channels, words 1 / 3 are the
@@ -1131,9 +1088,6 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                                        !((ref4[h >> 3] >> (4 * (h & 7) + my_group)) & 1u));         // nobody in MY warp group (warp-uniform)
                     int redo = -1;                      // a slot of mine that needs the warp-cooperative search
                     auto retarget = [&](int sl) { return lists_valid ? retarget_from_list(sl, h) : false; };
-                    // a compaction moves slots: no lookup is left pending across one
-                    const bool defer_ok = MCL_DEFER_RETARGET && lists_valid && same_channels && !verify_skip &&
-                                          !((n_slots - n_e) * TOMB_DIV > n_slots && n_slots >= 64);
                     auto scan = [&](auto two_targets) {
                         constexpr bool TWO = decltype(two_targets)::value;
                         constexpr int NWORD = SPC * (int)sizeof(NearT) / 4;       // 32-bit words of near[] per chunk
@@ -1183,12 +1137,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                                     const uint32_t nn = near[sl];
                                     if ((nn == (uint32_t)h || (TWO && nn == (uint32_t)h2)) && sl != smin && lone) atomicOr(&s_err, 1);
                                     if ((nn == (uint32_t)h || (TWO && nn == (uint32_t)h2)) && sl != smin) {
-                                        if (defer_ok && pend < 0) {
-                                            // request the list now, look at it after the next sweep: the round trip leaves the step's critical path
-                                            pend = sl; pend_h = h; cr[sl] = F_INF;
-                                            asm volatile("prefetch.global.L1 [%0];" :: "l"(cand_d + sl));
-                                            asm volatile("prefetch.global.L1 [%0];" :: "l"(cand_j + (size_t)sl * KC));
-                                        } else if (!retarget(sl)) {
+                                        if (!retarget(sl)) {
                                             // rare: park it until the warp search below
                                             if (redo >= 0) cr[sl] = -1.0f;      // more than one: mark, found again below
                                             else redo = sl;

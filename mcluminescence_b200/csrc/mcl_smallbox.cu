@@ -8,7 +8,7 @@
 // Why its own kernel: in the block kernel (mcl_philox.cu) such a replica is latency-bound on a serial chain -- a
 // 300-instruction step loop built for 10^4-electron boxes, grid searches that are chains of dependent L2 round trips,
 // candidate lists that fills invalidate.  Here the whole box lives on chip:
-//   * electrons in REGISTERS: lane l owns slots 4l..4l+3 (distance to the cached nearest hole, that hole's slot, the
+//   * electrons in REGISTERS: lane l owns slots l, l+32, l+64, l+96 (distance to the cached nearest hole, that hole's slot, the
 //     coordinates): no shared memory and no barrier for anything per-electron; "which of my electrons cached the dead
 //     hole" is four register compares;
 //   * holes in SHARED memory as three float arrays (12 bytes per hole); every nearest-hole search is a brute-force pass
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
     int nh[4];
     int birth[4];                  // creation order (legacy semantics: the OLDEST electron is the one that recombines)
 #pragma unroll
-    for (int k = 0; k < 4; k++) { c[k] = F_INF; nh[k] = -1; px[k] = py[k] = pz[k] = 0.f; birth[k] = 4 * lane + k; }
+    for (int k = 0; k < 4; k++) { c[k] = F_INF; nh[k] = -1; px[k] = py[k] = pz[k] = 0.f; birth[k] = lane + 32 * k; }
     int next_birth = rp.n_e0;
 
     if (status == MCL_OK) {
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int i = 4 * lane + k;
+            const int i = lane + 32 * k;
             if (i < n_e) {
                 uint32_t c0 = (uint32_t)i, c1 = 0u, c2 = rid_lo, c3 = rid_hi | (DOM_SEED_E << 28);
                 philox4x32_10(c0, c1, c2, c3, K);
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
         __syncwarp();
         // Box._rebuild (engine.py:113-119): nearest hole of every electron
         for (int i = 0; i < n_e; i++) {
-            const int own = i >> 2, k = i & 3;
+            const int own = i & 31, k = i >> 5;
             const float sx = pick4(px[0], px[1], px[2], px[3], k), sy = pick4(py[0], py[1], py[2], py[3], k),
                         sz = pick4(pz[0], pz[1], pz[2], pz[3], k);
             const float x = __shfl_sync(0xffffffffu, sx, own), y = __shfl_sync(0xffffffffu, sy, own), z = __shfl_sync(0xffffffffu, sz, own);
@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
         // ---------------- per-electron clocks (engine.py:65-77, tl_trap_lab.py:51), log2 domain
         float best = F_INF;
         int bslot = 0x7fffffff;
-        if (4 * lane < n_slots) {
+        const int kmax = (n_slots + 31) >> 5;            // slot s lives in lane s & 31, register row s >> 5: rows in use
+        if (kmax > 0) {
             uint32_t w0 = (uint32_t)lane, w1 = (uint32_t)rec_i, w2 = rid_lo, w3 = rid_hi | (DOM_STEP1 << 28);
             philox4x32_10(w0, w1, w2, w3, K);
             const uint32_t w[4] = {w0, w1, w2, w3};
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
+                if (k >= kmax) break;                           // warp-uniform: register rows beyond the slots in use hold nothing
                 const float le = lg2_fast(-lg2_fast(u01(w[k])));
                 const float Ak = ((ch2 >> k) & 1u) ? A2 : A1;
                 float l;
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
                 } else {
                     l = (le + c[k]) - Ak;
                 }
-                if (l < best) { best = l; bslot = 4 * lane + k; }
+                if (l < best) { best = l; bslot = lane + 32 * k; }
             }
         }
         // ---------------- warp argmin; equal clocks go to the smaller slot
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
             uint32_t fm = 0u;                                   // lowest free electron slot
 #pragma unroll
             for (int k = 0; k < 4; k++) fm |= !(c[k] < F_INF) ? (1u << k) : 0u;
-            const int es = (int)warp_min_u32(fm ? (uint32_t)(4 * lane + __ffs(fm) - 1) : 0x7fffffffu);
+            const int es = (int)warp_min_u32(fm ? (uint32_t)(lane + 32 * (__ffs(fm) - 1)) : 0x7fffffffu);
             if (es >= 124 || hs >= hcap) { status = MCL_ERR_CAPACITY; return false; }
             float cnew = sqrtf(d2);
             int jn = j;
@@ -287,8 +289,8 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
                     if (c[k] < F_INF && dd < c[k]) { c[k] = dd; nh[k] = hs; }
                 }
             }
-            if (lane == (es >> 2)) {
-                const int k = es & 3;
+            if (lane == (es & 31)) {
+                const int k = es >> 5;
                 set4(c, k, cnew); set4(nh, k, jn); set4(px, k, nx); set4(py, k, ny); set4(pz, k, nz); set4(birth, k, next_birth);
             }
             if (lane == 0) { hx[hs] = qx; hy[hs] = qy; hz[hs] = qz; }
@@ -308,10 +310,10 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
             if (legacy) {                    // the oldest alive electron
                 uint32_t key = 0xffffffffu;
 #pragma unroll
-                for (int k = 0; k < 4; k++) if (c[k] < F_INF) key = min(key, ((uint32_t)birth[k] << 7) | (uint32_t)(4 * lane + k));
+                for (int k = 0; k < 4; k++) if (c[k] < F_INF) key = min(key, ((uint32_t)birth[k] << 7) | (uint32_t)(lane + 32 * k));
                 victim = (int)(warp_min_u32(key) & 127u);
             }
-            const int own = victim >> 2, ks = victim & 3;
+            const int own = victim & 31, ks = victim >> 5;
             const int hsel = pick4(nh[0], nh[1], nh[2], nh[3], ks);
             const int h = __shfl_sync(0xffffffffu, hsel, own);
             if (lane == own) { set4(c, ks, F_INF); set4(nh, ks, -1); }
