@@ -63,6 +63,7 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
     int ne_max = 0, nh_max = 0, seg_max = 1;
     bool any_dose = false;
     L->small.clear(); L->big.clear(); L->small_hcap = 0;
+    L->small.reserve((size_t)a->n_replicas);
     bool small_ok = a->mode == MCL_MODE_PHILOX && !a->hist && !a->kind && !a->e_idx && !a->h_idx;
     if (const char *env = getenv("MCL_SMALLBOX")) small_ok = small_ok && atoi(env) != 0;       // test knob: 0 = block kernel for every replica
     for (int r = 0; r < a->n_replicas; r++) {

@@ -6,7 +6,10 @@
 //   (src/class/optimizer.py:49-84, src/class/tl_trap_lab.py:27-43,65-123,125-179).
 // Geometry is derived with the reference's own expressions in C doubles (Python's float `**` is
 // C pow), so int() truncations agree with the Python host path.
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -32,11 +35,6 @@ double numpy_sum(const double *a, size_t n)
     return numpy_sum(a, n2) + numpy_sum(a + n2, n - n2);
 }
 
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    bool alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess; }
-};
 
 // The scratch slab of an Optimizer population is gigabytes; allocating and freeing it on every call
 // costs anything from 1 ms to 0.5 s.  It is kept (grow-only, per device) between calls and handed back
@@ -98,6 +96,16 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
     // One call at a time: concurrent callers would run kernels in the same cached slab (and a larger request
     // would free it under the other call).  Documented in mcl_b200.h.
     std::lock_guard<std::mutex> call_lock(g_scratch.call_mu);
+    // MCL_OBJECTIVE_TIMING=1: wall-clock breakdown of the call on stderr (tables / plan / scratch / launch / wait / mse)
+    const bool timing = getenv("MCL_OBJECTIVE_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    double t_ms[6] = {0, 0, 0, 0, 0, 0};
+    auto lap = [&](int i) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        t_ms[i] = std::chrono::duration<double, std::milli>(now - t_prev).count();
+        t_prev = now;
+    };
     std::vector<mcl_replica> reps(R);
     std::vector<mcl_segment> segs(lab->rows, lab->rows + n_rows);
     for (int k = 0; k < n_rows; k++) {
@@ -142,9 +150,10 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
         if (iso) for (int o = 0; o < n_obs; o++) obs[(size_t)c * n_obs + o] = lab->obs_time[o];
     }
 
-    DevBuf d_final, d_obs, d_esteps, d_status;
-    if (!d_final.alloc(sizeof(int32_t) * R) || !d_esteps.alloc(sizeof(int64_t) * R) || !d_status.alloc(sizeof(int32_t) * R) ||
-        !d_obs.alloc(sizeof(int32_t) * obs.size())) { set_error("mcl_objective: cudaMalloc failed"); return MCL_ERR_ALLOC; }
+    // the per-replica outputs are carved from the cached scratch slab too (behind mcl_run's own workspace): no cudaMalloc
+    // / cudaFree on the call path (a cudaFree synchronises the device and was seen to take hundreds of milliseconds)
+    const size_t o_final = 0, o_status = align_up(o_final + sizeof(int32_t) * R, 256), o_esteps = align_up(o_status + sizeof(int32_t) * R, 256),
+                 o_obs = align_up(o_esteps + sizeof(int64_t) * R, 256), out_bytes = align_up(o_obs + sizeof(int32_t) * obs.size(), 256);
     mcl_run_args a;
     memset(&a, 0, sizeof(a));
     a.replicas = reps.data(); a.n_replicas = (int32_t)R;
@@ -152,15 +161,22 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
     a.obs_time = iso ? obs.data() : nullptr; a.n_obs = (int32_t)obs.size();
     a.max_steps = lab->max_steps; a.mode = MCL_MODE_PHILOX;
     a.seed = seed; a.replica_id0 = candidate_id0 * (uint64_t)n_rows;
-    a.final_n_e = (int32_t *)d_final.p; a.esteps = (int64_t *)d_esteps.p; a.status = (int32_t *)d_status.p;
-    a.obs_n_e = iso ? (int32_t *)d_obs.p : nullptr;
     a.stream = stream;
+    lap(0);
     size_t need = 0;
     PlannedRun *plan = mcl_plan(&a, &need);
+    lap(1);
     if (!plan) return MCL_ERR_ARG;
-    void *scratch = g_scratch.get(need);
-    if (!scratch) { mcl_plan_discard(plan); set_error("mcl_objective: cudaMalloc(workspace %zu) failed", need); return MCL_ERR_ALLOC; }
+    need = align_up(need, 256);
+    void *scratch = g_scratch.get(need + out_bytes);
+    if (!scratch) { mcl_plan_discard(plan); set_error("mcl_objective: cudaMalloc(workspace %zu) failed", need + out_bytes); return MCL_ERR_ALLOC; }
     a.workspace = scratch; a.workspace_bytes = need;
+    unsigned char *outs = (unsigned char *)scratch + need;
+    int32_t *d_final = (int32_t *)(outs + o_final), *d_status = (int32_t *)(outs + o_status), *d_obs = (int32_t *)(outs + o_obs);
+    int64_t *d_esteps = (int64_t *)(outs + o_esteps);
+    a.final_n_e = d_final; a.esteps = d_esteps; a.status = d_status;
+    a.obs_n_e = iso ? d_obs : nullptr;
+    lap(2);
     // kernel time of this call (H2D of the tables excluded), for the benchmark's roofline line
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     const bool timed = cudaEventCreate(&ev0) == cudaSuccess && cudaEventCreate(&ev1) == cudaSuccess;
@@ -168,12 +184,13 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
     int rc = mcl_run_planned(&a, plan, timed ? (void *)ev0 : nullptr, timed ? (void *)ev1 : nullptr);
     if (rc) { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); return rc; }
 
+    lap(3);
     std::vector<int32_t> final_n(R), status(R), obs_n(obs.size());
     std::vector<int64_t> est(R);
-    cudaMemcpyAsync(final_n.data(), d_final.p, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(status.data(), d_status.p, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(est.data(), d_esteps.p, sizeof(int64_t) * R, cudaMemcpyDeviceToHost, st);
-    if (iso) cudaMemcpyAsync(obs_n.data(), d_obs.p, sizeof(int32_t) * obs.size(), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(final_n.data(), d_final, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(status.data(), d_status, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(est.data(), d_esteps, sizeof(int64_t) * R, cudaMemcpyDeviceToHost, st);
+    if (iso) cudaMemcpyAsync(obs_n.data(), d_obs, sizeof(int32_t) * obs.size(), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (timed) {
         float ms = 0.f;
@@ -183,6 +200,7 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
     if (ev1) cudaEventDestroy(ev1);
     if (e != cudaSuccess) { set_error("mcl_objective: %s", cudaGetErrorString(e)); return MCL_ERR_CUDA; }
 
+    lap(4);
     int64_t total = 0;
     std::vector<double> se((size_t)(iso ? n_obs : n_rows));
     for (int c = 0; c < S; c++) {
@@ -207,6 +225,9 @@ extern "C" int mcl_objective(const double *P, int32_t S, const mcl_lab *lab, uin
         mse[c] = numpy_sum(se.data(), se.size()) / (double)se.size();
     }
     if (esteps_total) *esteps_total = total;
+    lap(5);
+    if (timing) fprintf(stderr, "mcl_objective S=%d: tables+alloc %.2f ms, plan %.2f, scratch %.2f, upload+launch %.2f, kernel+download %.2f (kernel %.2f), mse %.2f\n",
+                        S, t_ms[0], t_ms[1], t_ms[2], t_ms[3], t_ms[4], g_last_kernel_ms, t_ms[5]);
     return MCL_OK;
 }
 
