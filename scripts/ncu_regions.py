@@ -3,8 +3,8 @@ import csv, io, re, subprocess, sys
 rep = sys.argv[1]
 src = open("mcluminescence_b200/csrc/mcl_philox.cu").read().split("\n")
 # region boundaries: lines that start a region (first match wins, in file order)
-marks = [("helpers/philox", r"^constexpr uint32_t PHILOX_M0"), ("warp searches", r"^struct Holes"),
-         ("CTA barrier (cta_sync)", r"^__device__ __forceinline__ void cta_sync"), ("kernel setup", r"^template <int NT, int MINB, typename NearT, int PPC>"), ("seed holes", r"Box.seed \(engine.py:124-129\): holes"),
+marks = [("warp searches", r"^struct Holes"),
+         ("CTA barrier (cta_sync)", r"^__device__ __forceinline__ void cta_sync"), ("kernel setup", r"^template <int NT, int MINB, typename NearT, int PPC, bool SLAB_SMEM = false, bool REGRID = true>"), ("seed holes", r"Box.seed \(engine.py:124-129\): holes"),
          ("seed electrons + sort", r"electrons, stored in grid-cell order"), ("K-nearest init", r"^// Seeding, part 3 \(Box._rebuild"), ("K-nearest init (call site)", r"Box._rebuild \(engine.py:113-119\): the KC nearest holes of every electron \(kept"),
          ("leg setup", r"per-replica constants of the rate law"), ("step top", r"// ---------------- loop condition"),
          ("sweep", r"per-electron clocks \+ running argmin"), ("reduce+B1", r"// warp argmin -> one row per warp"),
@@ -32,6 +32,9 @@ for r in rows:
         ln, s_, i_ = int(r[0]), int(r[isamp] or 0), int(r[iex] or 0)
     except ValueError:
         continue
+    if cur_file.endswith("mcl_rng.cuh"):
+        a = agg.setdefault("helpers/philox", [0, 0]); a[0] += s_; a[1] += i_
+        continue
     if not cur_file.endswith("mcl_philox.cu"):
         a = agg.setdefault("(cuda headers: sync/shuffle/atomics)", [0, 0]); a[0] += s_; a[1] += i_
         continue
@@ -40,5 +43,5 @@ for r in rows:
         if ln >= st: name = nm
     a = agg.setdefault(name, [0, 0]); a[0] += s_; a[1] += i_
 ts = sum(a[0] for a in agg.values()); ti = sum(a[1] for a in agg.values())
-for st, nm in [(0, "before")] + starts + [(0, "(cuda headers: sync/shuffle/atomics)")]:
+for st, nm in [(0, "before"), (0, "helpers/philox")] + starts + [(0, "(cuda headers: sync/shuffle/atomics)")]:
     if nm in agg: print(f"{nm:24s} inst {100*agg[nm][1]/ti:5.1f}%   samples {100*agg[nm][0]/ts:5.1f}%")
