@@ -366,7 +366,7 @@ def main():
                     "frac": hbm_bytes / kern_s / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": hbm_bytes},
         }
         cpu, side = None, None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:          # the CPU baseline rides on the N = 1 line only
             from oracle import mcl_oracle as mo
             threads = mo.max_threads()
             n_units = cpu_sample_units(args.workload, threads)

@@ -134,24 +134,36 @@ static int plan_layout(const mcl_run_args *a, Layout *L)
             for (auto &b : bucket) for (int32_t r : b) list[o2++] = r;
         };
         order_list(L->big);
-        // small boxes: by capacity class first, longest work first inside a class
+        // small boxes: by capacity class first, longest work first inside a class -- one pass into (class, weight) buckets
         L->small_classes.clear();
-        std::vector<int32_t> all_small;
-        all_small.swap(L->small);
-        for (int cap : kSmallClassCaps) {
-            std::vector<int32_t> cls;
-            int hmax = 0;
-            for (int32_t r : all_small) {
+        if (!L->small.empty()) {
+            constexpr int NCLS = (int)(sizeof(kSmallClassCaps) / sizeof(kSmallClassCaps[0]));
+            const bool few = distinct.size() <= 64;
+            std::vector<double> d(distinct);
+            std::sort(d.begin(), d.end(), std::greater<double>());
+            const size_t nw = few ? d.size() : 1;
+            std::vector<std::vector<int32_t>> bucket((size_t)NCLS * nw);
+            int hmax[NCLS] = {0};
+            for (int32_t r : L->small) {
                 const int hc = smallbox_hole_capacity(a->replicas[r]);
-                bool mine = hc <= cap;
-                for (int c2 : kSmallClassCaps) { if (c2 >= cap) break; if (hc <= c2) { mine = false; break; } }
-                if (mine) { cls.push_back(r); hmax = std::max(hmax, hc); }
+                int cls = 0;
+                while (cls < NCLS - 1 && hc > kSmallClassCaps[cls]) cls++;
+                const size_t wb = few ? (size_t)(std::find(d.begin(), d.end(), w[r]) - d.begin()) : 0;
+                bucket[(size_t)cls * nw + wb].push_back(r);
+                hmax[cls] = std::max(hmax[cls], hc);
             }
-            if (cls.empty()) continue;
-            order_list(cls);
-            const int b = (int)L->small.size();
-            L->small.insert(L->small.end(), cls.begin(), cls.end());
-            L->small_classes.push_back(Layout::SmallClass{b, (int)L->small.size(), hmax});
+            L->small.clear();
+            for (int cls = 0; cls < NCLS; cls++) {
+                const int b = (int)L->small.size();
+                for (size_t wb = 0; wb < nw; wb++) {
+                    auto &v = bucket[(size_t)cls * nw + wb];
+                    L->small.insert(L->small.end(), v.begin(), v.end());
+                }
+                const int e = (int)L->small.size();
+                if (e == b) continue;
+                if (!few) std::stable_sort(L->small.begin() + b, L->small.begin() + e, [&](int32_t x, int32_t y) { return w[x] > w[y]; });
+                L->small_classes.push_back(Layout::SmallClass{b, e, hmax[cls]});
+            }
         }
     }
     L->total = o;
