@@ -103,6 +103,8 @@ struct Cfg {
     int fill_extra;    // fill-region slots beyond N_e: a fill that finds N_e + fill_extra of them in use regrids first
     int has_regrid;    // the slab has the regrid scratch (launches with a dosed leg somewhere)
     int relist;        // 1: a dose-free simulate leg that follows fills regrids and rebuilds the candidate lists
+    int pipe;          // 1: isothermal legs that qualify for the specialised loop run its pipelined form (wide CTAs; same results)
+    int off_pipe;      // byte offset (dynamic shared memory) of the sweep team's per-thread minima; inside ref4[] when that is large enough
     // shared-memory slab (small boxes): word offsets from the start of dynamic shared memory
     int sm_hpos, sm_exyz, sm_cstart, sm_cfill;
 };
@@ -258,6 +260,35 @@ __device__ __forceinline__ void cta_sync()
 {
     if (NT > 32) __syncthreads(); else __syncwarp();
 }
+
+// Named barriers of the pipelined step loop (ids 1..4; __syncthreads is barrier 0): the producer side arrives without waiting,
+// the consumer side waits -- PTX's producer / consumer pattern.  `n` counts ALL participating threads (arrivers + waiters).
+// (immediate ids: with an id in a register ptxas reserves all 16 barriers for the CTA)
+template <int ID> __device__ __forceinline__ void named_sync_id(int n) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
+template <int ID> __device__ __forceinline__ void named_arrive_id(int n) { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
+constexpr int BAR_FULL = 1, BAR_DONE = 3;      // + step parity
+__device__ __forceinline__ void named_sync(int id, int n)
+{
+    if (id == 1) named_sync_id<1>(n); else if (id == 2) named_sync_id<2>(n); else if (id == 3) named_sync_id<3>(n); else named_sync_id<4>(n);
+}
+__device__ __forceinline__ void named_arrive(int id, int n)
+{
+    if (id == 1) named_arrive_id<1>(n); else if (id == 2) named_arrive_id<2>(n); else if (id == 3) named_arrive_id<3>(n); else named_arrive_id<4>(n);
+}
+
+#ifdef MCL_PIPE_STATS
+// Profiling build only: [0] steps applied by the pipelined loop, [1] entries, [2] hand-backs: leg end / max steps, [3] compaction
+// due, [4] filling clock, [5] hit overflow, [6] repair sweeps (a row whose winner was a stale slot), [7] steps with a scan,
+// [8] hits, [9] warp searches
+// [16..] cycles: sweep team (warp 0): 16 sweep, 17 wait DONE, 18 entry + arrive; decision warp: 20 wait FULL, 22 minimum +
+// re-evaluations, 23 decision + event (up to DONE), 24 histogram
+__device__ unsigned long long g_pipe[32];
+#define MCL_PSTAT(i, v) { if (lane == 0) atomicAdd(&g_pipe[i], (unsigned long long)(v)); }
+#define MCL_PTIME(i) { const long long now_ = clock64(); if (lane == 0 && (warp == 0 || warp == NW - 1)) atomicAdd(&g_pipe[i], (unsigned long long)(now_ - pt_)); pt_ = now_; }
+#else
+#define MCL_PSTAT(i, v)
+#define MCL_PTIME(i)
+#endif
 
 // NearT: type of the per-electron nearest-hole slot kept in shared memory.  uint16_t whenever the
 // hole capacity allows (halves the footprint and the traffic of the post-event scan); the all-ones
@@ -437,6 +468,11 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     __shared__ double rec_t[32];
     __shared__ int s_scan[33];
     __shared__ int s_err;              // self-check failures (verify mode)
+    // pipelined loop: per step parity, what the decision warp tells the sweep team (-2: step handed back, leave; -1: go on),
+    // and the state handed back at the end
+    __shared__ int s_cmd[2], s_pipe_i[4];
+    __shared__ double s_pipe_d[2];
+    __shared__ long long s_pipe_ll;
     if (threadIdx.x == 0) s_err = 0;
 
     // ---------------- HBM slab
@@ -750,7 +786,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     // New nearest hole of slot `sl` from its candidate list: the first remembered candidate that is still alive and is not
     // `h_dead` (the hole dying in the event at hand, whose bitmap bit may not be visible yet).  Distances and slots are
     // fetched together: ONE round trip to L2 / HBM.  false: list exhausted.
-    auto retarget_from_list = [&](int sl, int h_dead) -> bool {
+    auto retarget_from_list = [&](int sl, int h_dead, bool mark = true) -> bool {
         const float4 d4 = cand_d[sl];
         uint32_t cj[KC];
         if (sizeof(NearT) == 2) {
@@ -767,7 +803,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             const uint32_t j = cj[c];
             if (!fixed && j != NEAR_DEAD && j != (uint32_t)h_dead && ((hole_bm[j >> 5] >> (j & 31)) & 1u)) {
                 cr[sl] = dk[c]; near[sl] = (NearT)j; fixed = true;
-                if (share_bm && !ever_filled) mark_target(j, sl);
+                if (mark && share_bm && !ever_filled) mark_target(j, sl);
             }
         }
         return fixed;
@@ -833,7 +869,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         // hole was ever added -- what BASELINE-sized ensembles run; protocol, dose, trace and fill-mode branches are compiled
         // out, which shortens the serial part of a step (C2 +6.7 %, C5 +9.3 %).  The general loop takes over, repeating the
         // step in hand, the moment the filling clock could matter.  Same records either way (scripts/compare_libs.py).
-        auto step_loop = [&](auto fast_tag) -> bool {         // true: leg finished (or error), false: continue in the general loop
+        // Returns 0: leg finished (or error), 1: continue in the general loop, 2: `budget` steps done (the pipelined loop asked
+        // for a step in order; budget < 0: no limit).
+        auto step_loop = [&](auto fast_tag, int budget) -> int {
             constexpr bool FAST = decltype(fast_tag)::value;
             const bool lab_o = lab, iso_o = iso, trace_o = trace, dose_o = dose_on, verify_o = verify_skip;
             if (FAST) { __builtin_assume(!ever_filled); __builtin_assume(lists_valid_); }
@@ -1008,7 +1046,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 if (FAST && !(fminf(dt_rec0, dt_cap) < 3.0e12f)) {
                     // the filling clock could matter (spurious fill): the general loop repeats this step
                     cta_sync<NT>();
-                    return false;
+                    return 1;
                 }
                 if (dose_on || !((lab ? dt_rec0 : fminf(dt_rec0, dt_cap)) < 3.0e12f)) {       // (the lab loops have no step cap)
                     float lam = (n_e == rp.N_e || !dose_on) ? 1e-20f : dose_over_D0 * (float)(rp.N_e - n_e);
@@ -1288,13 +1326,317 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     }
                 }
                 if (!lab && S.duration != 0.0 && t_cur >= S.duration) break;          // simulate.py:91-92
+                if (FAST && --budget == 0) return 2;
             }
             }
-            return true;
+            return 0;
 #undef lists_valid
         };
-        if (!(MCL_FAST_LOOP && cfg.fast && !lab && !trace && !verify_skip && !dose_on && !ever_filled && step_loop(std::true_type{})))
-            step_loop(std::false_type{});
+
+        // ---------------- The specialised loop, PIPELINED (isothermal legs, wide CTAs).  In the loop above a warp sweeps, waits for
+        // the slowest warp, and then EVERY warp walks the same ~300-instruction decision / event path before the next sweep
+        // can start: more than half of a step is serial.  Here the roles are split: warps 0 .. NW-2 (the sweep team) SWEEP
+        // step k+1 while the last warp DECIDES step k and applies its event.  Two facts make that exact:
+        //  * At constant temperature the clocks of step k+1 depend on event k only through the slots the event touches, and
+        //    clocks are counter-based (slot, step): whoever re-evaluates a slot gets THE clock the loop in order would use.
+        //  * LAZY RE-TARGETING.  An electron cached on a hole that has died keeps its stale (smaller) distance, so its clock
+        //    is a LOWER BOUND of the true one (same draw, larger rate).  If it does not win the step with the bound it cannot
+        //    win with the true clock either, so nothing has to be done; if it does win, the decision warp re-targets it
+        //    (candidate list, else a grid search), re-evaluates the clocks of the thread that reported it and takes the
+        //    minimum again.  No post-event scan, no sharing masks; each step's winner and waiting time are those of the
+        //    loop in order (an exact FP32 tie at the minimum may go to the other slot).
+        //   sweep team:     sweep(k) -> wait DONE[k-1] -> its best (clock, slot) per THREAD -> arrive FULL[k]
+        //   decision warp:  wait FULL[k] -> minimum of the team's entries -> winner retired while the sweep ran, stale, or
+        //                   written while the sweep ran?  re-evaluate that thread's chunks, again -> decision -> event ->
+        //                   arrive DONE[k] -> histograms
+        // Steps the pipeline cannot take (compaction due, last step of the leg, filling clock relevant) are handed back BEFORE
+        // anything of them is applied; on the way out every stale electron is re-targeted and the sharing masks are rebuilt, so
+        // the loop in order finds the state it would have produced itself.
+        constexpr bool PIPE_K = NT >= 128 && !SLAB_SMEM;
+        auto pipe_loop = [&]() -> int {               // returns the number of steps it took
+            constexpr int NTS = PIPE_K ? NT - 32 : 32, DW = NW - 1;         // (narrow CTAs never come here: PIPE_K)
+            constexpr unsigned FULLM = 0xffffffffu;
+            if (!PIPE_K) return 0;
+            const int k0 = rec_i;
+            const int n_chunks = (n_slots + SPC - 1) / SPC;
+            const bool one = (A1 == A2);
+            float2 *team_best = reinterpret_cast<float2 *>(smem_raw + cfg.off_pipe);      // [NTS] (clock, slot bits); may alias ref4[]
+            // raw clocks (identical channels without a conduction-band term: before the uniform prefactor A1 is subtracted)
+            // of chunks b_first, b_first + stride, ... : the expressions of pair_loop
+            auto sweep_impl = [&](auto with_cb, auto one_channel, int b_first, int stride, int step, float &best, int &bslot) {
+                constexpr bool CB = decltype(with_cb)::value;
+                constexpr bool ONE = decltype(one_channel)::value;
+                const float4 *cr4 = reinterpret_cast<const float4 *>(cr);
+                if constexpr (ONE) {
+                    auto chunks = [&](auto n_chains, int b0) {
+                        constexpr int NCH = decltype(n_chains)::value;
+                        float cs[NCH][4];
+                        uint32_t w[NCH][4];
+#pragma unroll
+                        for (int q = 0; q < NCH; q++) {
+                            const int b = b0 + q * stride;
+                            const float4 cq = cr4[b];
+                            cs[q][0] = cq.x; cs[q][1] = cq.y; cs[q][2] = cq.z; cs[q][3] = cq.w;
+                            w[q][0] = (uint32_t)b; w[q][1] = (uint32_t)step; w[q][2] = rid_lo; w[q][3] = rid_hi | (DOM_STEP1 << 28);
+                        }
+#pragma unroll
+                        for (int q = 0; q < NCH; q++) philox4x32_10(w[q][0], w[q][1], w[q][2], w[q][3], K);
+#pragma unroll
+                        for (int q = 0; q < NCH; q++) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const float le = lg2_fast(-lg2_fast(u01(w[q][k])));
+                                float l;
+                                if (CB) {
+                                    const float a = A1 - cs[q][k];
+                                    const float kk = fmaxf(a, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a - g)));
+                                    l = (le - kk) + (cs[q][k] - cs[q][k]);
+                                } else {
+                                    l = le + cs[q][k];
+                                }
+                                if (l < best) { best = l; bslot = 4 * (b0 + q * stride) + k; }
+                            }
+                        }
+                    };
+                    int b0 = b_first;
+                    for (; b0 + (MCL_ONE_CHAINS - 1) * stride < n_chunks; b0 += MCL_ONE_CHAINS * stride)
+                        chunks(std::integral_constant<int, MCL_ONE_CHAINS>{}, b0);
+                    for (; b0 < n_chunks; b0 += stride) chunks(std::integral_constant<int, 1>{}, b0);
+                } else {
+                    for (int b = b_first; b < n_chunks; b += stride) {
+                        float cs[SPC];
+                        const float4 cq = cr4[b];
+                        cs[0] = cq.x; cs[1] = cq.y; cs[2] = cq.z; cs[3] = cq.w;
+                        float l[SPC];
+#pragma unroll
+                        for (int i = 0; i < PPC; i++) {
+                            uint32_t c0 = (uint32_t)(PPC * b + i), c1 = (uint32_t)step, c2 = rid_lo, c3 = rid_hi | (DOM_STEP << 28);
+                            philox4x32_10(c0, c1, c2, c3, K);
+                            const float a0 = ((c0 < thr) ? A2 : A1) - cs[2 * i];
+                            const float a1 = ((c2 < thr) ? A2 : A1) - cs[2 * i + 1];
+                            const float le0 = lg2_fast(-lg2_fast(u01(c1)));
+                            const float le1 = lg2_fast(-lg2_fast(u01(c3)));
+                            if (CB) {
+                                const float k0_ = fmaxf(a0, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a0 - g)));
+                                const float k1_ = fmaxf(a1, g) + lg2_fast(1.0f + ex2_fast(-fabsf(a1 - g)));
+                                l[2 * i] = (le0 - k0_) + (cs[2 * i] - cs[2 * i]);
+                                l[2 * i + 1] = (le1 - k1_) + (cs[2 * i + 1] - cs[2 * i + 1]);
+                            } else {
+                                l[2 * i] = le0 - a0;
+                                l[2 * i + 1] = le1 - a1;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < SPC; i++) if (l[i] < best) { best = l[i]; bslot = SPC * b + i; }
+                    }
+                }
+            };
+            auto sweep = [&](int b_first, int stride, int step, float &best, int &bslot) {
+                if (one) { if (has_cb) sweep_impl(std::true_type{}, std::true_type{}, b_first, stride, step, best, bslot); else sweep_impl(std::false_type{}, std::true_type{}, b_first, stride, step, best, bslot); }
+                else     { if (has_cb) sweep_impl(std::true_type{}, std::false_type{}, b_first, stride, step, best, bslot); else sweep_impl(std::false_type{}, std::false_type{}, b_first, stride, step, best, bslot); }
+            };
+            auto hole_alive = [&](uint32_t j) { return ((hole_bm[j >> 5] >> (j & 31)) & 1u) != 0u; };
+
+            if (tid == 0) { s_cmd[0] = s_cmd[1] = -1; }
+            cta_sync<NT>();
+            MCL_PSTAT(1, warp == DW)
+#ifdef MCL_PIPE_STATS
+            long long pt_ = clock64();
+#endif
+            if (warp != DW) {
+                // ===== the sweep team
+                for (int k = k0;; k++) {
+                    const int par = k & 1;
+                    float best = F_INF; int bslot = -1;
+                    sweep(tid, NTS, k, best, bslot);
+                    MCL_PTIME(16)
+                    if (k > k0) {
+                        named_sync(BAR_DONE + (par ^ 1), NT);             // step k-1 is applied (or handed back); its entries have been read
+                        if (s_cmd[par ^ 1] == -2) break;
+                    }
+                    MCL_PTIME(17)
+                    team_best[tid] = make_float2(best, __int_as_float(bslot));
+                    __threadfence_block();
+                    named_arrive(BAR_FULL + par, NT);
+                    MCL_PTIME(18)
+                }
+            } else {
+                // ===== the decision warp
+                constexpr int NQ = PIPE_K ? DW : 1;   // entries per lane: thread lane + 32 q of the team
+                int f_prev = -1, f_cur = -1;          // lane i: the i-th slot re-targeted in the previous / in this step (written while a sweep ran)
+                int nf_cur = 0;
+                int k = k0;
+                for (;;) {
+                    const int par = k & 1;
+                    named_sync(BAR_FULL + par, NT);
+                    MCL_PTIME(20)
+                    int hand_back = 0;
+                    float ev_[NQ]; int es_[NQ];
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) { const float2 e = team_best[lane + 32 * q]; ev_[q] = e.x; es_[q] = __float_as_int(e.y); }
+                    f_prev = f_cur; f_cur = -1; nf_cur = 0;
+                    uint32_t fresh = 0u;              // bit q: my entry q was re-evaluated in this step, from the state as it is
+                    float vraw; int smin;
+                    for (;;) {
+                        float v = ev_[0]; int s_ = es_[0], q_ = 0;
+#pragma unroll
+                        for (int q = 1; q < NQ; q++) if (ev_[q] < v) { v = ev_[q]; s_ = es_[q]; q_ = q; }
+                        vraw = warp_min_f32(v);
+                        const unsigned m = __ballot_sync(FULLM, v == vraw);
+                        const int src = m ? (__ffs(m) - 1) : 0;
+                        smin = __shfl_sync(FULLM, s_, src);
+                        const int qw = __shfl_sync(FULLM, q_, src);
+                        if (smin < 0) break;                                          // no clock anywhere
+                        const bool is_fresh = (__shfl_sync(FULLM, fresh, src) >> qw) & 1u;
+                        bool again = false;
+                        if (!(cr[smin] < F_INF)) {
+                            again = true;                                             // retired while the sweep ran
+                        } else if (!hole_alive(near[smin])) {
+                            // a stale electron wins with its lower bound: re-target it now
+                            bool ok = true;
+                            if (lane == 0) ok = retarget_from_list(smin, -1, false);
+                            ok = __shfl_sync(FULLM, (int)ok, 0) != 0;
+                            if (!ok) {
+                                const unsigned long long b = warp_nearest(H, ex[smin], ey[smin], ez[smin], lane);
+                                if (lane == 0) { cr[smin] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[smin] = (NearT)(uint32_t)b; }
+                                MCL_PSTAT(9, 1)
+                            }
+                            __syncwarp();
+                            if (lane == nf_cur) f_cur = smin;
+                            nf_cur++;
+                            again = true;
+                            MCL_PSTAT(8, 1)
+                        } else if (!is_fresh) {
+                            for (unsigned mm = __ballot_sync(FULLM, f_prev >= 0); mm; mm &= mm - 1) again |= (smin == __shfl_sync(FULLM, f_prev, __ffs(mm) - 1));
+                        }
+                        if (!again) break;
+                        if (nf_cur >= 32) { hand_back = 5; break; }
+                        // the clocks of the thread that reported it, from the state as it is: one chunk per lane
+                        const int t = src + 32 * qw;
+                        float b_ = F_INF; int bs_ = -1;
+                        sweep(t + lane * NTS, 32 * NTS, k, b_, bs_);
+                        const float wv = warp_min_f32(b_);
+                        const unsigned m2 = __ballot_sync(FULLM, b_ == wv);
+                        const int ws_ = __shfl_sync(FULLM, bs_, m2 ? (__ffs(m2) - 1) : 0);
+                        if (lane == src) {
+#pragma unroll
+                            for (int q = 0; q < NQ; q++) if (q == qw) { ev_[q] = wv; es_[q] = ws_; }
+                            fresh |= 1u << qw;
+                        }
+                        MCL_PSTAT(6, 1)
+                    }
+                    MCL_PTIME(22)
+                    // ---------------- decision: the expressions of the loop in order (dt_fill = inf, no fill)
+                    const float vmin = (one && !has_cb) ? vraw - A1 : vraw;
+                    const int hmin = smin >= 0 ? (int)near[smin] : -1;
+                    const float dt_rec0 = ex2_fast(vmin) * LN2F;               // n_e > 0 in this loop
+                    const float dt = fminf(dt_rec0, dt_cap);
+                    const bool is_rec = (dt == dt_rec0);
+                    const double t_new = t_cur + (double)dt;
+                    if (!hand_back) {
+                        if (!(dt < 3.0e12f) || smin < 0) hand_back = 4;                                   // the filling clock could matter
+                        else if (!(t_new < S.duration) || k + 1 >= p.max_steps) hand_back = 2;            // last step of the leg
+                        else if (is_rec && ((n_slots - n_e + 1) * TOMB_DIV > n_slots || n_e - 1 < 4 * NT)) hand_back = 3;   // compaction due
+                    }
+                    if (hand_back) {
+                        MCL_PSTAT(hand_back, 1)
+                        if (lane == 0) s_cmd[par] = -2;
+                        __threadfence_block();
+                        named_arrive(BAR_DONE + par, NT);
+                        break;
+                    }
+                    // ---------------- apply
+                    es32 += (uint32_t)n_e;
+                    if (es32 > 0xC0000000u) { esteps += es32; es32 = 0u; }
+                    const int n_before = n_e;
+                    if (is_rec) {
+                        const int h = hmin;
+                        if (lane == 0) {
+                            cr[smin] = F_INF; near[smin] = (NearT)NEAR_DEAD;
+                            hpos[h].x = DEAD_X;
+                            hole_bm[h >> 5] &= ~(1u << (h & 31));
+                        }
+                        n_e--;
+                    }
+                    if (lane == 0) s_cmd[par] = -1;
+                    __threadfence_block();
+                    named_arrive(BAR_DONE + par, NT);
+                    MCL_PTIME(23)
+                    // ---------------- fused histograms (off the sweep team's critical path)
+                    if (hedge_next <= t_new) {
+                        while (hedge_next <= t_new) {
+                            if (lane == 0 && p.hist_occ && hbin_next < p.hist.n_bins) {
+                                size_t q = (size_t)hrow * p.hist.n_bins + hbin_next;
+                                atomicAdd(&p.hist_occ[q], (unsigned long long)n_before);
+                                if (p.hist_occ_sq) atomicAdd(&p.hist_occ_sq[q], (unsigned long long)n_before * (unsigned long long)n_before);
+                            }
+                            hbin_next++;
+                            hedge_next = hbin_next <= p.hist.n_bins ? edge_after(hbin_next, hedge_next) : CUDART_INF;
+                        }
+                    }
+                    t_cur = t_new;
+                    if (is_rec && lane == 0 && hist_on && p.hist_events) {
+                        const int b = h_mono ? (hbin_next - 1) : bin_of(t_cur);
+                        if (b >= 0 && b < p.hist.n_bins) atomicAdd(&p.hist_events[(size_t)hrow * p.hist.n_bins + b], 1ull);
+                    }
+                    k++;
+                    MCL_PTIME(24)
+                    MCL_PSTAT(0, 1)
+                }
+                if (lane == 0) {
+                    s_pipe_d[0] = t_cur; s_pipe_d[1] = hedge_next; s_pipe_ll = esteps;
+                    s_pipe_i[0] = hbin_next; s_pipe_i[1] = n_e; s_pipe_i[2] = k; s_pipe_i[3] = (int)es32;
+                }
+            }
+            cta_sync<NT>();
+            t_cur = s_pipe_d[0]; hedge_next = s_pipe_d[1]; esteps = s_pipe_ll;
+            hbin_next = s_pipe_i[0]; n_e = s_pipe_i[1]; rec_i = s_pipe_i[2]; es32 = (uint32_t)s_pipe_i[3];
+            draws_valid = false;
+            // ---------------- on the way out: every electron still cached on a dead hole is re-targeted (the loop in order keeps
+            // no stale electron), then the sharing masks are counted afresh (team_best may have lived in ref4[])
+            for (int base = 0; base < n_slots; base += NT) {
+                const int sl = base + tid;
+                bool ok = true;
+                if (sl < n_slots) { const uint32_t nn = near[sl]; if (nn != NEAR_DEAD && !hole_alive(nn)) ok = retarget_from_list(sl, -1, false); }
+                for (unsigned need = __ballot_sync(FULLM, !ok); need; need &= need - 1) {
+                    const int src = __ffs(need) - 1;
+                    const int sl2 = __shfl_sync(FULLM, sl, src);
+                    const unsigned long long b = warp_nearest(H, ex[sl2], ey[sl2], ez[sl2], lane);
+                    if (lane == src) { cr[sl2] = sqrtf(__uint_as_float((uint32_t)(b >> 32))); near[sl2] = (NearT)(uint32_t)b; }
+                }
+            }
+            if (share_bm) {
+                for (int w = tid; w < cfg.bm_words + cfg.ref_words; w += NT) multi_bm[w] = 0u;
+                cta_sync<NT>();
+                for (int sl = tid; sl < n_slots; sl += NT) { const uint32_t j = near[sl]; if (j != NEAR_DEAD) mark_target(j, sl); }
+            }
+            cta_sync<NT>();
+            return rec_i - k0;
+        };
+
+        {
+            const bool fast_ok = MCL_FAST_LOOP && cfg.fast && !lab && !trace && !verify_skip && !dose_on && !ever_filled;
+            int rc = 1;
+            if (fast_ok) {
+                // Pipelined while it pays: the pipeline hands back before every step it cannot take (compaction due, end of
+                // the leg, ...), that ONE step runs in order, and it starts again; a leg on which it keeps handing back after
+                // a few steps (a depleted box whose events re-target dozens of electrons) finishes in order.  (One call site
+                // per loop: they must stay inlined, their state in registers.)
+                const bool use_pipe = PIPE_K && cfg.pipe && T_const && (!REGRID || lists_valid_);
+                int short_runs = 0;
+                for (;;) {
+                    int budget = -1;
+                    if (use_pipe && n_e >= 4 * NT && short_runs < 8) {
+                        const int done = pipe_loop();
+                        short_runs = done < 8 ? short_runs + 1 : 0;
+                        budget = 1;
+                    }
+                    rc = step_loop(std::true_type{}, budget);
+                    if (rc != 2) break;
+                }
+            }
+            if (rc == 1) step_loop(std::false_type{}, -1);
+        }
         t_off += t_cur;
         if (lab) break;
     }
@@ -1355,6 +1697,16 @@ extern "C" int mcl_debug_exp_draws(const uint32_t *words, int32_t n, float *neg_
     return rc;
 }
 
+#ifdef MCL_PIPE_STATS
+extern "C" int mcl_debug_pipe_stats(unsigned long long *out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_pipe, sizeof(unsigned long long) * 32);
+    if (reset) { static unsigned long long z[32]; cudaMemcpyToSymbol(g_pipe, z, sizeof(z)); }
+    return (int)e;
+}
+#endif
+
 #ifdef MCL_PROFILE_SKEW
 extern "C" int mcl_debug_prof(unsigned long long *out, int reset)
 {
@@ -1373,7 +1725,7 @@ static int grid_edge_max(int n_h0_max)
 
 struct PhiloxPlan {
     int nt; int cap_slots; int g_max; int cap_cells; int bm_words; int share_bm; int ref_words; size_t smem; size_t off_holes; size_t off_cand;
-    size_t off_hpos2, off_hmap; size_t stride; bool near16;
+    size_t off_hpos2, off_hmap; size_t stride; bool near16; int off_pipe;
     bool slab_smem; int sm_hpos, sm_exyz, sm_cstart, sm_cfill;
 };
 
@@ -1414,7 +1766,18 @@ static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override, int n_replica
     if (const char *env = getenv("MCL_PHILOX_SHARE_BM")) { int v = atoi(env); pl.share_bm = v < 0 ? 0 : (v > 2 ? 2 : v); }   // knob: 0 off, 1 on, 2 on + self-check
     pl.ref_words = (cap_h + 7) / 8;
     if (nt < 256) pl.share_bm = 0;
+    // pipelined loop: (clock, slot) of every sweep-team thread.  It is idle whenever ref4[] is in use and the other way
+    // round (the masks are counted afresh when the pipeline hands back), so a large enough ref4[] doubles as its storage --
+    // 10^4-electron boxes have no shared memory to spare at three CTAs per SM.
+    pl.off_pipe = 0;
+    if (nt >= 128) {
+        const size_t need = 8 * (size_t)(nt - 32);
+        const size_t ref_off = align_up(pl.smem + 4 * (size_t)pl.bm_words, 8);
+        if (pl.share_bm && ref_off + need <= pl.smem + 4 * ((size_t)pl.bm_words + (size_t)pl.ref_words)) pl.off_pipe = (int)ref_off;
+        else { pl.off_pipe = (int)align_up(pl.smem + (pl.share_bm ? 4 * ((size_t)pl.bm_words + (size_t)pl.ref_words) : 0), 8); }
+    }
     if (pl.share_bm) pl.smem += 4 * ((size_t)pl.bm_words + (size_t)pl.ref_words);
+    if (nt >= 128 && (size_t)pl.off_pipe + 8 * (size_t)(nt - 32) > pl.smem) pl.smem = (size_t)pl.off_pipe + 8 * (size_t)(nt - 32);
     // Small boxes (one warp per replica): hole table, cell tables and electron coordinates in shared memory when at least
     // four such CTAs fit an SM.  MCL_PHILOX_SMEM_SLAB=0 keeps them in the HBM slab (same results; test knob).
     pl.slab_smem = false; pl.sm_hpos = pl.sm_exyz = pl.sm_cstart = pl.sm_cfill = 0;
@@ -1466,9 +1829,11 @@ cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_
     if (const char *env = getenv("MCL_PHILOX_FAST")) fast = atoi(env) != 0;        // knob: 0 = general step loop only
     int fill_extra = kFillExtra, relist = 1;
     if (const char *env = getenv("MCL_PHILOX_FILL_EXTRA")) { int v = atoi(env); fill_extra = v > kFillExtra ? kFillExtra : v; }   // test knob: regrid early (may be negative)
+    int pipe = 1;
+    if (const char *env = getenv("MCL_PHILOX_PIPE")) pipe = atoi(env) != 0;        // knob: 0 = isothermal legs run the specialised loop in order
     if (const char *env = getenv("MCL_PHILOX_RELIST")) relist = atoi(env) != 0;    // knob: 0 = read-out legs after fills keep searching the grid
     Cfg cfg{pl.cap_slots, pl.g_max, pl.cap_cells, pl.bm_words, pl.share_bm, pl.ref_words, pl.off_holes, pl.off_cand, fast,
-            pl.off_hpos2, pl.off_hmap, fill_extra, p.with_regrid != 0, relist, pl.sm_hpos, pl.sm_exyz, pl.sm_cstart, pl.sm_cfill};
+            pl.off_hpos2, pl.off_hmap, fill_extra, p.with_regrid != 0, relist, pipe, pl.off_pipe, pl.sm_hpos, pl.sm_exyz, pl.sm_cstart, pl.sm_cfill};
     const RoundKeys K = make_round_keys(p.seed);
     // MINB caps the register count at 64 per thread (32 resident warps per SM when smem allows)
 #define MCL_CASE(NT_, MINB_, PPC_)                                                                  \

@@ -319,6 +319,51 @@ def test_specialised_step_loop_changes_no_result(gpu):
     assert 0 < int(fast.final_n_e.max()) < int(jobs[-1]["replicas"]["n_e0"][0]) // 2
 
 
+def test_pipelined_step_loop_changes_no_result(gpu):
+    """Isothermal legs of wide CTAs run the specialised loop PIPELINED: a sweep team computes the clocks of step k+1 while
+    one warp decides step k, electrons cached on a dead hole are re-targeted lazily (only when they win a step with their
+    stale lower bound), and steps the pipeline cannot take (compaction due, end of a leg, filling clock, a box running
+    empty) are handed back and run in order.  `MCL_PHILOX_PIPE=0` runs the same legs in order: histograms, final
+    occupancies, step and electron-step counts and status codes must be equal, replica for replica."""
+    import os
+    from mcluminescence_b200 import engine, workloads
+    two = ["physics_fp.E_loc_2=1.0", "physics_fp.Retrap=0.3"]
+    capped = workloads.c2(n_replicas=6, n_e=3000, n_bins=50)
+    capped["segments"]["dt_cap"] = [0.25, 1e20]                 # most steps of the hold leg end at the cap: no event
+    capped["max_steps"] = 30000
+    short = workloads.c2(n_replicas=6, n_e=3000, n_bins=50)
+    short["max_steps"] = 700                                    # MCL_ERR_STEPS in the middle of the first leg
+    jobs = [("c2, 512 threads", workloads.c2(n_replicas=12), None),
+            ("c2, 256 threads", workloads.c2(n_replicas=6), 256),
+            ("c2 two channels", workloads.c2(n_replicas=6, n_e=5000, physics_overrides=two), 256),
+            ("c2 2000 electrons, 128 threads", workloads.c2(n_replicas=24, n_e=2000, n_bins=50), 128),
+            # conduction-band channel on (every clock takes the 4-SFU form); the boxes run nearly empty, so the legs end in order
+            ("c2 conduction band", workloads.c2(n_replicas=8, n_e=3000, n_bins=50, physics_overrides=["physics_fp.E_cb=1.5"]), 256),
+            ("c2 conduction band + two channels", workloads.c2(n_replicas=8, n_e=3000, n_bins=50, physics_overrides=["physics_fp.E_cb=1.5"] + two), 128),
+            ("c2 step cap", capped, 256), ("c2 out of steps", short, 256)]
+    took_pipeline = False
+    for name, wl, nt in jobs:
+        def go(pipe):
+            os.environ["MCL_PHILOX_PIPE"] = pipe
+            if nt:
+                os.environ["MCL_PHILOX_NT"] = str(nt)
+            try:
+                return engine.run_replicas(wl["replicas"], wl["segments"], wl["max_steps"], seed=43, hist=wl["hist"], trace=False, sync=True)
+            finally:
+                os.environ.pop("MCL_PHILOX_PIPE", None); os.environ.pop("MCL_PHILOX_NT", None)
+        a, b = go("1"), go("0")
+        for k in ("status", "steps_used", "final_n_e", "esteps", "hist_events", "hist_occ"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), f"{name}: {k}"
+        if name == "c2 out of steps":
+            assert np.all(a.status != 0)
+        else:
+            a.raise_on_error()
+        if name == "c2 conduction band":
+            assert int(a.final_n_e.max()) < 1024               # below 4 x 256: the legs cannot have ended inside the pipeline
+        took_pipeline |= bool(a.steps_used.min() > 1000)
+    assert took_pipeline
+
+
 def test_shared_memory_slab_changes_no_result(gpu, capsys):
     """Small boxes (the Optimizer path) keep their hole table, cell tables and electron coordinates in shared memory;
     `MCL_PHILOX_SMEM_SLAB=0` keeps them in the HBM slab.  Same algorithm: every objective value and electron-step
