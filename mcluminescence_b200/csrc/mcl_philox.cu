@@ -59,6 +59,11 @@ namespace {
 // smallest slot wins whatever the width (exact launch-shape invariance) at a measured 2.3 % of C2's throughput (6.20e11
 // vs 6.06e11: one more branch in each of the two serial reduction stages of every step).  Either way the result is a valid
 // sample; only bit-identity across CTA widths is at stake.  Default: 1.
+// How many sweeps the sweep team of the pipelined loop may be ahead of the decision warp (a power of two, <= 4: one named
+// barrier and one set of per-thread minima per step in flight).
+#ifndef MCL_PIPE_DEPTH
+#define MCL_PIPE_DEPTH 2
+#endif
 #ifndef MCL_OLD_TIEBREAK
 #define MCL_OLD_TIEBREAK 1
 #endif
@@ -266,7 +271,7 @@ __device__ __forceinline__ void cta_sync()
 // (immediate ids: with an id in a register ptxas reserves all 16 barriers for the CTA)
 template <int ID> __device__ __forceinline__ void named_sync_id(int n) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
 template <int ID> __device__ __forceinline__ void named_arrive_id(int n) { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
-constexpr int BAR_FULL = 1, BAR_DONE = 3;      // + step parity
+constexpr int BAR_FULL = 1;                    // + step % depth
 __device__ __forceinline__ void named_sync(int id, int n)
 {
     if (id == 1) named_sync_id<1>(n); else if (id == 2) named_sync_id<2>(n); else if (id == 3) named_sync_id<3>(n); else named_sync_id<4>(n);
@@ -283,6 +288,8 @@ __device__ __forceinline__ void named_arrive(int id, int n)
 // [16..] cycles: sweep team (warp 0): 16 sweep, 17 wait DONE, 18 entry + arrive; decision warp: 20 wait FULL, 22 minimum +
 // re-evaluations, 23 decision + event (up to DONE), 24 histogram
 __device__ unsigned long long g_pipe[32];
+__device__ unsigned long long g_pipe_h[4][8];    // [0]/[1]: count / cycles of decision-warp steps (FULL -> next FULL wait) by duration bucket; [2]/[3]: the same for warp 0's flag waits
+__device__ __forceinline__ int pipe_bucket(long long c) { return c < 3000 ? 0 : c < 4500 ? 1 : c < 6000 ? 2 : c < 8000 ? 3 : c < 12000 ? 4 : c < 20000 ? 5 : c < 40000 ? 6 : 7; }
 #define MCL_PSTAT(i, v) { if (lane == 0) atomicAdd(&g_pipe[i], (unsigned long long)(v)); }
 #define MCL_PTIME(i) { const long long now_ = clock64(); if (lane == 0 && (warp == 0 || warp == NW - 1)) atomicAdd(&g_pipe[i], (unsigned long long)(now_ - pt_)); pt_ = now_; }
 #else
@@ -456,7 +463,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     const bool verify_skip = SHARE_K && cfg.share_bm == 2;     // test mode: scan anyway and flag a hit that the masks ruled out
     constexpr int GROUP_SHIFT = NW >= 4 ? (NW == 4 ? 0 : (NW == 8 ? 1 : 2)) : 0;      // warps per group = NW / 4 (NW >= 4)
     const int my_group = min(3, warp >> GROUP_SHIFT);
-    auto group_of_slot = [&](int sl) { return min(3, (((sl >> 2) & (NT - 1)) >> 5) >> GROUP_SHIFT); };   // owner = chunk % NT
+    auto group_of_slot = [&](int sl) { return min(3, (((sl >> 2) % NT) >> 5) >> GROUP_SHIFT); };   // owner = chunk % NT
     auto mark_target = [&](uint32_t j, int sl) {
         const int sh = 4 * (j & 7);
         const uint32_t old_ = atomicOr(&ref4[j >> 3], 1u << (sh + group_of_slot(sl)));
@@ -468,8 +475,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
     __shared__ double rec_t[32];
     __shared__ int s_scan[33];
     __shared__ int s_err;              // self-check failures (verify mode)
-    // pipelined loop: per step parity, what the decision warp tells the sweep team (-2: step handed back, leave; -1: go on),
-    // and the state handed back at the end
+    // pipelined loop: s_cmd[0] = how far the decision warp has got (the sweep team polls it), and the state handed back at the end
     __shared__ int s_cmd[2], s_pipe_i[4];
     __shared__ double s_pipe_d[2];
     __shared__ long long s_pipe_ll;
@@ -1345,22 +1351,29 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         //    (candidate list, else a grid search), re-evaluates the clocks of the thread that reported it and takes the
         //    minimum again.  No post-event scan, no sharing masks; each step's winner and waiting time are those of the
         //    loop in order (an exact FP32 tie at the minimum may go to the other slot).
-        //   sweep team:     sweep(k) -> wait DONE[k-1] -> its best (clock, slot) per THREAD -> arrive FULL[k]
+        //   sweep team:     sweep(k) -> wait until step k-2 is done (a flag) -> its best (clock, slot) per THREAD -> arrive FULL[k]
         //   decision warp:  wait FULL[k] -> minimum of the team's entries -> winner retired while the sweep ran, stale, or
         //                   written while the sweep ran?  re-evaluate that thread's chunks, again -> decision -> event ->
-        //                   arrive DONE[k] -> histograms
+        //                   step k done (flag) -> histograms
         // Steps the pipeline cannot take (compaction due, last step of the leg, filling clock relevant) are handed back BEFORE
         // anything of them is applied; on the way out every stale electron is re-targeted and the sharing masks are rebuilt, so
         // the loop in order finds the state it would have produced itself.
+        // Ramps qualify too while both channels are identical and the conduction-band term is off: the clocks are then
+        // lg2(-lg2 u) + cr - A1(T), the temperature enters as ONE uniform offset, and the sweep does not need it at all.
+        // (64-thread CTAs -- one sweep warp, one decision warp -- measured slower than their loop in order: C5 3.22e11 vs 3.40e11.)
         constexpr bool PIPE_K = NT >= 128 && !SLAB_SMEM;
         auto pipe_loop = [&]() -> int {               // returns the number of steps it took
+            // (Measured, no gain: a double share of chunks for the team warp that shares a scheduler with the decision warp -- it
+            // took twice as long, 7.74e11 -> 7.09e11; CTAs of 288 threads = 8 team warps + the decision warp at 72 registers:
+            // 7.93e11 vs 7.85e11; the team 4 sweeps ahead instead of 2; a named barrier or a sleeping poll instead of the spin.)
             constexpr int NTS = PIPE_K ? NT - 32 : 32, DW = NW - 1;         // (narrow CTAs never come here: PIPE_K)
+            constexpr int DEPTH = MCL_PIPE_DEPTH;
             constexpr unsigned FULLM = 0xffffffffu;
             if (!PIPE_K) return 0;
             const int k0 = rec_i;
             const int n_chunks = (n_slots + SPC - 1) / SPC;
             const bool one = (A1 == A2);
-            float2 *team_best = reinterpret_cast<float2 *>(smem_raw + cfg.off_pipe);      // [NTS] (clock, slot bits); may alias ref4[]
+            float2 *team_best = reinterpret_cast<float2 *>(smem_raw + cfg.off_pipe);      // [DEPTH][NTS] (clock, slot bits); may alias ref4[]
             // raw clocks (identical channels without a conduction-band term: before the uniform prefactor A1 is subtracted)
             // of chunks b_first, b_first + stride, ... : the expressions of pair_loop
             auto sweep_impl = [&](auto with_cb, auto one_channel, int b_first, int stride, int step, float &best, int &bslot) {
@@ -1437,7 +1450,8 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             };
             auto hole_alive = [&](uint32_t j) { return ((hole_bm[j >> 5] >> (j & 31)) & 1u) != 0u; };
 
-            if (tid == 0) { s_cmd[0] = s_cmd[1] = -1; }
+            volatile int *s_done = &s_cmd[0];       // steps < s_done are applied; -(j+1): step j was handed back
+            if (tid == 0) s_cmd[0] = k0;
             cta_sync<NT>();
             MCL_PSTAT(1, warp == DW)
 #ifdef MCL_PIPE_STATS
@@ -1446,35 +1460,59 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             if (warp != DW) {
                 // ===== the sweep team
                 for (int k = k0;; k++) {
-                    const int par = k & 1;
+                    const int par = k & (DEPTH - 1);
                     float best = F_INF; int bslot = -1;
+                    const int d_early = *s_done;          // read before the sweep, looked at after it: usually step k-2 is long done
+#ifdef MCL_PIPE_STATS
+                    const long long sw0_ = clock64();
+#endif
                     sweep(tid, NTS, k, best, bslot);
+#ifdef MCL_PIPE_STATS
+                    if (lane == 0 && warp < 7) atomicAdd(&g_pipe[25 + warp], (unsigned long long)(clock64() - sw0_));     // [25..31]: sweep cycles of team warp 0..6
+#endif
                     MCL_PTIME(16)
-                    if (k > k0) {
-                        named_sync(BAR_DONE + (par ^ 1), NT);             // step k-1 is applied (or handed back); its entries have been read
-                        if (s_cmd[par ^ 1] == -2) break;
+                    if (k >= k0 + DEPTH) {
+                        // step k-2 applied (or handed back) and its entries read?  A flag, not a barrier: the team's warps
+                        // must not wait for each other here (they meet at FULL only through the decision warp).
+                        int d = d_early, a = d < 0 ? -d : d;
+#ifdef MCL_PIPE_STATS
+                        const long long fw0_ = clock64();
+#endif
+                        while (a < k - DEPTH + 1) { d = *s_done; a = d < 0 ? -d : d; }
+#ifdef MCL_PIPE_STATS
+                        if (lane == 0 && warp == 0) { const long long c_ = clock64() - fw0_; atomicAdd(&g_pipe_h[2][pipe_bucket(c_)], 1ull); atomicAdd(&g_pipe_h[3][pipe_bucket(c_)], (unsigned long long)c_); }
+#endif
+                        if (d < 0 && -d - 1 <= k - DEPTH) break;          // step -d-1 was handed back: leave
                     }
                     MCL_PTIME(17)
-                    team_best[tid] = make_float2(best, __int_as_float(bslot));
-                    __threadfence_block();
-                    named_arrive(BAR_FULL + par, NT);
+                    team_best[par * NTS + tid] = make_float2(best, __int_as_float(bslot));
+                    named_arrive(BAR_FULL + par, NT);                     // (barrier instructions order the shared-memory accesses before them)
                     MCL_PTIME(18)
                 }
             } else {
                 // ===== the decision warp
                 constexpr int NQ = PIPE_K ? DW : 1;   // entries per lane: thread lane + 32 q of the team
-                int f_prev = -1, f_cur = -1;          // lane i: the i-th slot re-targeted in the previous / in this step (written while a sweep ran)
+                // lane i: the i-th slot re-targeted in this step / 1 .. DEPTH steps ago (written while the sweep at hand may have run)
+                int f_cur = -1, f_old[DEPTH];
+#pragma unroll
+                for (int i = 0; i < DEPTH; i++) f_old[i] = -1;
                 int nf_cur = 0;
                 int k = k0;
                 for (;;) {
-                    const int par = k & 1;
+                    const int par = k & (DEPTH - 1);
                     named_sync(BAR_FULL + par, NT);
                     MCL_PTIME(20)
+#ifdef MCL_PIPE_STATS
+                    const long long dw0_ = clock64();
+#endif
                     int hand_back = 0;
+                    if (!T_const) { set_T(t_cur); if (has_cb) hand_back = 7; }      // (a ramp: the sweep team's clocks carry no temperature)
                     float ev_[NQ]; int es_[NQ];
 #pragma unroll
-                    for (int q = 0; q < NQ; q++) { const float2 e = team_best[lane + 32 * q]; ev_[q] = e.x; es_[q] = __float_as_int(e.y); }
-                    f_prev = f_cur; f_cur = -1; nf_cur = 0;
+                    for (int q = 0; q < NQ; q++) { const float2 e = team_best[par * NTS + lane + 32 * q]; ev_[q] = e.x; es_[q] = __float_as_int(e.y); }
+#pragma unroll
+                    for (int i = DEPTH - 1; i > 0; i--) f_old[i] = f_old[i - 1];
+                    f_old[0] = f_cur; f_cur = -1; nf_cur = 0;
                     uint32_t fresh = 0u;              // bit q: my entry q was re-evaluated in this step, from the state as it is
                     float vraw; int smin;
                     for (;;) {
@@ -1507,9 +1545,11 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                             again = true;
                             MCL_PSTAT(8, 1)
                         } else if (!is_fresh) {
-                            for (unsigned mm = __ballot_sync(FULLM, f_prev >= 0); mm; mm &= mm - 1) again |= (smin == __shfl_sync(FULLM, f_prev, __ffs(mm) - 1));
+#pragma unroll
+                            for (int i = 0; i < DEPTH; i++)
+                                for (unsigned mm = __ballot_sync(FULLM, f_old[i] >= 0); mm; mm &= mm - 1) again |= (smin == __shfl_sync(FULLM, f_old[i], __ffs(mm) - 1));
                         }
-                        if (!again) break;
+                        if (!again || hand_back) break;
                         if (nf_cur >= 32) { hand_back = 5; break; }
                         // the clocks of the thread that reported it, from the state as it is: one chunk per lane
                         const int t = src + 32 * qw;
@@ -1540,9 +1580,10 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     }
                     if (hand_back) {
                         MCL_PSTAT(hand_back, 1)
-                        if (lane == 0) s_cmd[par] = -2;
                         __threadfence_block();
-                        named_arrive(BAR_DONE + par, NT);
+                        if (lane == 0) *s_done = -(k + 1);
+                        // the team is up to DEPTH sweeps ahead: its entries of steps k+1 .. k+DEPTH-1 are on their way
+                        for (int i = 1; i < DEPTH; i++) named_sync(BAR_FULL + ((k + i) & (DEPTH - 1)), NT);
                         break;
                     }
                     // ---------------- apply
@@ -1558,9 +1599,8 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         }
                         n_e--;
                     }
-                    if (lane == 0) s_cmd[par] = -1;
                     __threadfence_block();
-                    named_arrive(BAR_DONE + par, NT);
+                    if (lane == 0) *s_done = k + 1;
                     MCL_PTIME(23)
                     // ---------------- fused histograms (off the sweep team's critical path)
                     if (hedge_next <= t_new) {
@@ -1580,6 +1620,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         if (b >= 0 && b < p.hist.n_bins) atomicAdd(&p.hist_events[(size_t)hrow * p.hist.n_bins + b], 1ull);
                     }
                     k++;
+#ifdef MCL_PIPE_STATS
+                    if (lane == 0) { const long long c_ = clock64() - dw0_; atomicAdd(&g_pipe_h[0][pipe_bucket(c_)], 1ull); atomicAdd(&g_pipe_h[1][pipe_bucket(c_)], (unsigned long long)c_); }
+#endif
                     MCL_PTIME(24)
                     MCL_PSTAT(0, 1)
                 }
@@ -1622,11 +1665,12 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                 // the leg, ...), that ONE step runs in order, and it starts again; a leg on which it keeps handing back after
                 // a few steps (a depleted box whose events re-target dozens of electrons) finishes in order.  (One call site
                 // per loop: they must stay inlined, their state in registers.)
-                const bool use_pipe = PIPE_K && cfg.pipe && T_const && (!REGRID || lists_valid_);
+                const bool use_pipe = PIPE_K && cfg.pipe && (T_const || A1 == A2) && (!REGRID || lists_valid_);
                 int short_runs = 0;
                 for (;;) {
                     int budget = -1;
-                    if (use_pipe && n_e >= 4 * NT && short_runs < 8) {
+                    if (use_pipe && !T_const) set_T(t_cur);
+                    if (use_pipe && (T_const || !has_cb) && n_e >= 4 * NT && short_runs < 8) {
                         const int done = pipe_loop();
                         short_runs = done < 8 ? short_runs + 1 : 0;
                         budget = 1;
@@ -1702,7 +1746,8 @@ extern "C" int mcl_debug_pipe_stats(unsigned long long *out, int reset)
 {
     cudaDeviceSynchronize();
     cudaError_t e = cudaMemcpyFromSymbol(out, g_pipe, sizeof(unsigned long long) * 32);
-    if (reset) { static unsigned long long z[32]; cudaMemcpyToSymbol(g_pipe, z, sizeof(z)); }
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out + 32, g_pipe_h, sizeof(unsigned long long) * 32);
+    if (reset) { static unsigned long long z[32]; cudaMemcpyToSymbol(g_pipe, z, sizeof(z)); cudaMemcpyToSymbol(g_pipe_h, z, sizeof(z)); }
     return (int)e;
 }
 #endif
@@ -1771,13 +1816,13 @@ static PhiloxPlan make_plan(int cap_e, int cap_h, int nt_override, int n_replica
     // 10^4-electron boxes have no shared memory to spare at three CTAs per SM.
     pl.off_pipe = 0;
     if (nt >= 128) {
-        const size_t need = 8 * (size_t)(nt - 32);
+        const size_t need = 8 * MCL_PIPE_DEPTH * (size_t)nt;
         const size_t ref_off = align_up(pl.smem + 4 * (size_t)pl.bm_words, 8);
         if (pl.share_bm && ref_off + need <= pl.smem + 4 * ((size_t)pl.bm_words + (size_t)pl.ref_words)) pl.off_pipe = (int)ref_off;
         else { pl.off_pipe = (int)align_up(pl.smem + (pl.share_bm ? 4 * ((size_t)pl.bm_words + (size_t)pl.ref_words) : 0), 8); }
     }
     if (pl.share_bm) pl.smem += 4 * ((size_t)pl.bm_words + (size_t)pl.ref_words);
-    if (nt >= 128 && (size_t)pl.off_pipe + 8 * (size_t)(nt - 32) > pl.smem) pl.smem = (size_t)pl.off_pipe + 8 * (size_t)(nt - 32);
+    if (nt >= 128 && (size_t)pl.off_pipe + 8 * MCL_PIPE_DEPTH * (size_t)nt > pl.smem) pl.smem = (size_t)pl.off_pipe + 8 * MCL_PIPE_DEPTH * (size_t)nt;
     // Small boxes (one warp per replica): hole table, cell tables and electron coordinates in shared memory when at least
     // four such CTAs fit an SM.  MCL_PHILOX_SMEM_SLAB=0 keeps them in the HBM slab (same results; test knob).
     pl.slab_smem = false; pl.sm_hpos = pl.sm_exyz = pl.sm_cstart = pl.sm_cfill = 0;
@@ -1840,7 +1885,9 @@ cudaError_t launch_philox(const LaunchParams &p, cudaStream_t stream, int /*max_
     case NT_:                                                                                      \
         return pl.near16 ? launch_one<NT_, MINB_, uint16_t, PPC_>(p, K, cfg, pl.smem, stream)      \
                          : launch_one<NT_, MINB_, uint32_t, PPC_>(p, K, cfg, pl.smem, stream)
-#ifdef MCL_ONLY_C2          // build-time probe (scripts/regs_probe.sh): only the BASELINE C2 instantiation, for quick ptxas -v runs
+#if defined(MCL_ONLY_NT)    // build-time probe: ONE instantiation (-DMCL_ONLY_NT=96 -DMCL_ONLY_MINB=6), for quick A/B builds; run it with MCL_PHILOX_NT set to the same width
+    return launch_two<MCL_ONLY_NT, MCL_ONLY_MINB, uint16_t, 2, false, false>(p, K, cfg, pl.smem, stream);
+#elif defined(MCL_ONLY_C2)  // build-time probe (scripts/regs_probe.sh): only the BASELINE C2 instantiation, for quick ptxas -v runs
     return launch_two<256, MCL_NT256_MINB, uint16_t, 2, false, false>(p, K, cfg, pl.smem, stream);
 #else
     if (pl.slab_smem)       // (implies nt == 32) few CTAs per SM: no register cap worth the name

@@ -11,7 +11,10 @@ marks = [("warp searches", r"^struct Holes"),
          ("scalar/dt", r"filling clock \(tl_trap_lab.py:53-60\) and dt"), ("histogram", r"fused occupancy histogram"),
          ("event: remove", r"Box.remove_pair \(engine.py:154-175\)"), ("scan+retarget", r"Which of MY other electrons"),
          ("compaction", r"compaction: keep tombstones"), ("fill", r"Box.add_electron \(engine.py:133-152\)"),
-         ("record/tail", r"record \(simulate.py:64,85-89\)")]
+         ("record/tail", r"record \(simulate.py:64,85-89\)"),
+         ("pipeline: clocks (sweep team + re-evaluations)", r"The specialised loop, PIPELINED"), ("pipeline: sweep team", r"===== the sweep team"),
+         ("pipeline: decision warp", r"===== the decision warp"), ("pipeline: way out (flush, masks)", r"on the way out: every electron"),
+         ("leg driver", r"const bool fast_ok = ")]
 starts = []
 for name, pat in marks:
     for i, l in enumerate(src):
@@ -44,4 +47,4 @@ for r in rows:
     a = agg.setdefault(name, [0, 0]); a[0] += s_; a[1] += i_
 ts = sum(a[0] for a in agg.values()); ti = sum(a[1] for a in agg.values())
 for st, nm in [(0, "before"), (0, "helpers/philox")] + starts + [(0, "(cuda headers: sync/shuffle/atomics)")]:
-    if nm in agg: print(f"{nm:24s} inst {100*agg[nm][1]/ti:5.1f}%   samples {100*agg[nm][0]/ts:5.1f}%")
+    if nm in agg: print(f"{nm:50s} inst {100*agg[nm][1]/ti:5.1f}%   samples {100*agg[nm][0]/ts:5.1f}%")

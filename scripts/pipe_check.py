@@ -30,15 +30,19 @@ def same(a, b, tag):
 ok = True
 jobs = [("c2 x12 nt256", workloads.c2(n_replicas=12), 256), ("c2 x6 nt512", workloads.c2(n_replicas=6), None),
         ("c2 two-channel 5000e", workloads.c2(n_replicas=6, n_e=5000, physics_overrides=["physics_fp.E_loc_2=1.0", "physics_fp.Retrap=0.3"]), 256),
-        ("c2 2000e nt128", workloads.c2(n_replicas=24, n_e=2000), 128), ("c2 x300", workloads.c2(n_replicas=300), None)]
+        ("c2 2000e nt128", workloads.c2(n_replicas=24, n_e=2000), 128), ("c2 x300", workloads.c2(n_replicas=300), None),
+        ("c5 x300 nt64", workloads.c5(n_replicas=300), 64), ("c5 x300 nt128", workloads.c5(n_replicas=300), 128), ("c5 x100 nt256", workloads.c5(n_replicas=100), 256)]
+if os.environ.get("ONLY256"):          # libraries built with -DMCL_ONLY_C2 hold the 256-thread kernel only
+    jobs = [j for j in jobs if j[2] == 256 or j[0] == "c2 x300"]
 for tag, wl, nt in jobs:
     a = run(wl, True, nt=nt); b = run(wl, False, nt=nt)
     ok &= same(a, b, tag)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2960
 wl = workloads.c2(n_replicas=n)
+nt_t = int(os.environ["TIME_NT"]) if os.environ.get("TIME_NT") else None
 for pipe in (1, 0, 1, 0):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    o = run(wl, pipe, seed=7)
+    o = run(wl, pipe, seed=7, nt=nt_t)
     dt = time.perf_counter() - t0
     print(f"pipe={pipe}: {int(np.asarray(o.esteps).sum()) / dt / 1e9:.1f} G electron-steps/s wall ({dt * 1e3:.0f} ms)", flush=True)
 sys.exit(0 if ok else 1)
