@@ -354,12 +354,22 @@ def main():
                     break
             except Exception:  # noqa: BLE001
                 pass
+        # A tighter bound from what the sweep of THIS workload actually issues per electron-step (SASS of the identical-channel
+        # sweep: one Philox4x32-10 call = 20 IMAD.WIDE per four electrons, 2 MUFU.LG2 each, 20.25 issue slots in all; two
+        # distinct channels: one call per two electrons).  The wide multiply is the scarce pipe (measured ~30 lanes/clk/SM).
+        two_ch = bool(os.environ.get("MCL_BENCH_TWO_CHANNEL")) or args.workload == "c4"
+        mix = {"imad_wide": 10.0 if two_ch else 5.0, "mufu": 2.0, "issue_slots": 30.0 if two_ch else 20.25}
+        peak_mix = min(peaks["imad_gops"] * 1e9 / mix["imad_wide"], peaks["mufu_gops"] * 1e9 / mix["mufu"],
+                       peaks["ffma_gops"] * 1e9 / mix["issue_slots"])
         roofline = {
             "bound": "sfu_fp32_issue", "achieved": achieved, "peak": peak_measured, "unit": UNIT,
             "frac": achieved / peak_measured, "traffic": traffic, "traffic_source": traffic_src,
-            "kernel": "philox_kernel", "model": f"{SFU_PER_ESTEP:g} SFU + {LANEOPS_PER_ESTEP:g} FP32/INT32 lane-ops per electron-step",
+            "kernel": "smallbox_kernel" if population else "philox_kernel",
+            "model": f"{SFU_PER_ESTEP:g} SFU + {LANEOPS_PER_ESTEP:g} FP32/INT32 lane-ops per electron-step (SURVEY 8d)",
             "peak_source": "mcl_device_peaks microbenchmarks in this run (MUFU, FFMA issue)",
             "peak_nominal": peak_nominal, "frac_nominal": achieved / peak_nominal,
+            "instruction_mix_bound": {"per_electron_step": mix, "peak": peak_mix, "frac": achieved / peak_mix,
+                                      "note": "min over the measured pipe rates of what the sweep issues per electron-step; the wide-multiply pipe binds"},
             "pipe_peaks_gops": {k: peaks[k] for k in ("mufu_gops", "ffma_gops", "imad_gops", "lop3_gops")},
             "sm_mhz_during": sm_hz / 1e6,
             "hbm": {"achieved_gbs": hbm_bytes / kern_s / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,

@@ -64,6 +64,9 @@ namespace {
 #ifndef MCL_PIPE_DEPTH
 #define MCL_PIPE_DEPTH 2
 #endif
+#ifndef MCL_PIPE_SLEEP
+#define MCL_PIPE_SLEEP 50
+#endif
 #ifndef MCL_OLD_TIEBREAK
 #define MCL_OLD_TIEBREAK 1
 #endif
@@ -1478,7 +1481,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
 #ifdef MCL_PIPE_STATS
                         const long long fw0_ = clock64();
 #endif
-                        while (a < k - DEPTH + 1) { d = *s_done; a = d < 0 ? -d : d; }
+                        // (a sleeping poll: a team that is held up by its decision warp -- small boxes -- must not take issue slots from it)
+                        if (a < k - DEPTH + 1) { d = *s_done; a = d < 0 ? -d : d; }
+                        while (a < k - DEPTH + 1) { __nanosleep(MCL_PIPE_SLEEP); d = *s_done; a = d < 0 ? -d : d; }
 #ifdef MCL_PIPE_STATS
                         if (lane == 0 && warp == 0) { const long long c_ = clock64() - fw0_; atomicAdd(&g_pipe_h[2][pipe_bucket(c_)], 1ull); atomicAdd(&g_pipe_h[3][pipe_bucket(c_)], (unsigned long long)c_); }
 #endif
