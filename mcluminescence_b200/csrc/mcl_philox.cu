@@ -1376,6 +1376,8 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
             const int k0 = rec_i;
             const int n_chunks = (n_slots + SPC - 1) / SPC;
             const bool one = (A1 == A2);
+            int4 *team_row = &red_row[0][0];                  // [DEPTH][NW]
+            static_assert(MCL_PIPE_DEPTH * NW <= 64, "team rows live in red_row[2][32]");
             float2 *team_best = reinterpret_cast<float2 *>(smem_raw + cfg.off_pipe);      // [DEPTH][NTS] (clock, slot bits); may alias ref4[]
             // raw clocks (identical channels without a conduction-band term: before the uniform prefactor A1 is subtracted)
             // of chunks b_first, b_first + stride, ... : the expressions of pair_loop
@@ -1473,6 +1475,10 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
 #ifdef MCL_PIPE_STATS
                     if (lane == 0 && warp < 7) atomicAdd(&g_pipe[25 + warp], (unsigned long long)(clock64() - sw0_));     // [25..31]: sweep cycles of team warp 0..6
 #endif
+                    const float wv = warp_min_f32(best);
+                    const unsigned wm_ = __ballot_sync(FULLM, best == wv);
+                    const int wl_ = wm_ ? (__ffs(wm_) - 1) : 0;
+                    const int ws_ = __shfl_sync(FULLM, bslot, wl_);
                     MCL_PTIME(16)
                     if (k >= k0 + DEPTH) {
                         // step k-2 applied (or handed back) and its entries read?  A flag, not a barrier: the team's warps
@@ -1490,19 +1496,27 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         if (d < 0 && -d - 1 <= k - DEPTH) break;          // step -d-1 was handed back: leave
                     }
                     MCL_PTIME(17)
+                    // every thread's minimum (read only when a winner has to be re-evaluated) and one row per warp (what the decision
+                    // warp reads every step): (clock, slot, the lane that reported it)
                     team_best[par * NTS + tid] = make_float2(best, __int_as_float(bslot));
+                    if (lane == 0) team_row[par * NW + warp] = make_int4(__float_as_int(wv), ws_, wl_, 0);
                     named_arrive(BAR_FULL + par, NT);                     // (barrier instructions order the shared-memory accesses before them)
                     MCL_PTIME(18)
                 }
             } else {
                 // ===== the decision warp
-                constexpr int NQ = PIPE_K ? DW : 1;   // entries per lane: thread lane + 32 q of the team
                 // lane i: the i-th slot re-targeted in this step / 1 .. DEPTH steps ago (written while the sweep at hand may have run)
                 int f_cur = -1, f_old[DEPTH];
 #pragma unroll
                 for (int i = 0; i < DEPTH; i++) f_old[i] = -1;
                 int nf_cur = 0;
                 int k = k0;
+                unsigned ev_acc = 0u;                 // events since the histogram cursor last moved (monotonic axes)
+                auto flush_events = [&]() {
+                    const int b = hbin_next - 1;
+                    if (ev_acc && lane == 0 && b >= 0 && b < p.hist.n_bins) atomicAdd(&p.hist_events[(size_t)hrow * p.hist.n_bins + b], (unsigned long long)ev_acc);
+                    ev_acc = 0u;
+                };
                 for (;;) {
                     const int par = k & (DEPTH - 1);
                     named_sync(BAR_FULL + par, NT);
@@ -1512,25 +1526,21 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
 #endif
                     int hand_back = 0;
                     if (!T_const) { set_T(t_cur); if (has_cb) hand_back = 7; }      // (a ramp: the sweep team's clocks carry no temperature)
-                    float ev_[NQ]; int es_[NQ];
-#pragma unroll
-                    for (int q = 0; q < NQ; q++) { const float2 e = team_best[par * NTS + lane + 32 * q]; ev_[q] = e.x; es_[q] = __float_as_int(e.y); }
+                    float v = F_INF; int s_ = -1, l_ = 0;             // lane w < DW: the row of team warp w
+                    if (lane < DW) { const int4 row = team_row[par * NW + lane]; v = __int_as_float(row.x); s_ = row.y; l_ = row.z; }
 #pragma unroll
                     for (int i = DEPTH - 1; i > 0; i--) f_old[i] = f_old[i - 1];
                     f_old[0] = f_cur; f_cur = -1; nf_cur = 0;
-                    uint32_t fresh = 0u;              // bit q: my entry q was re-evaluated in this step, from the state as it is
+                    uint32_t fresh = 0u;              // bit w: thread (w, my lane) of the team was re-evaluated in this step, from the state as it is
                     float vraw; int smin;
                     for (;;) {
-                        float v = ev_[0]; int s_ = es_[0], q_ = 0;
-#pragma unroll
-                        for (int q = 1; q < NQ; q++) if (ev_[q] < v) { v = ev_[q]; s_ = es_[q]; q_ = q; }
                         vraw = warp_min_f32(v);
                         const unsigned m = __ballot_sync(FULLM, v == vraw);
-                        const int src = m ? (__ffs(m) - 1) : 0;
-                        smin = __shfl_sync(FULLM, s_, src);
-                        const int qw = __shfl_sync(FULLM, q_, src);
+                        const int wsrc = m ? (__ffs(m) - 1) : 0;                      // the team warp that reported the minimum ...
+                        smin = __shfl_sync(FULLM, s_, wsrc);
+                        const int tl = __shfl_sync(FULLM, l_, wsrc);                  // ... and its lane
                         if (smin < 0) break;                                          // no clock anywhere
-                        const bool is_fresh = (__shfl_sync(FULLM, fresh, src) >> qw) & 1u;
+                        const bool is_fresh = (__shfl_sync(FULLM, fresh, tl) >> wsrc) & 1u;
                         bool again = false;
                         if (!(cr[smin] < F_INF)) {
                             again = true;                                             // retired while the sweep ran
@@ -1556,18 +1566,22 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         }
                         if (!again || hand_back) break;
                         if (nf_cur >= 32) { hand_back = 5; break; }
-                        // the clocks of the thread that reported it, from the state as it is: one chunk per lane
-                        const int t = src + 32 * qw;
+                        // the clocks of the thread that reported it, from the state as it is (one chunk per lane), then that
+                        // warp's row again from its threads' entries
+                        const int t = 32 * wsrc + tl;
                         float b_ = F_INF; int bs_ = -1;
                         sweep(t + lane * NTS, 32 * NTS, k, b_, bs_);
-                        const float wv = warp_min_f32(b_);
-                        const unsigned m2 = __ballot_sync(FULLM, b_ == wv);
-                        const int ws_ = __shfl_sync(FULLM, bs_, m2 ? (__ffs(m2) - 1) : 0);
-                        if (lane == src) {
-#pragma unroll
-                            for (int q = 0; q < NQ; q++) if (q == qw) { ev_[q] = wv; es_[q] = ws_; }
-                            fresh |= 1u << qw;
-                        }
+                        const float tv = warp_min_f32(b_);
+                        const unsigned m2 = __ballot_sync(FULLM, b_ == tv);
+                        const int ts_ = __shfl_sync(FULLM, bs_, m2 ? (__ffs(m2) - 1) : 0);
+                        if (lane == tl) { team_best[par * NTS + t] = make_float2(tv, __int_as_float(ts_)); fresh |= 1u << wsrc; }
+                        __syncwarp();
+                        const float2 e = team_best[par * NTS + 32 * wsrc + lane];
+                        const float wv = warp_min_f32(e.x);
+                        const unsigned m3 = __ballot_sync(FULLM, e.x == wv);
+                        const int wl_ = m3 ? (__ffs(m3) - 1) : 0;
+                        const int ws_ = __shfl_sync(FULLM, __float_as_int(e.y), wl_);
+                        if (lane == wsrc) { v = wv; s_ = ws_; l_ = wl_; }
                         MCL_PSTAT(6, 1)
                     }
                     MCL_PTIME(22)
@@ -1597,18 +1611,16 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     const int n_before = n_e;
                     if (is_rec) {
                         const int h = hmin;
-                        if (lane == 0) {
-                            cr[smin] = F_INF; near[smin] = (NearT)NEAR_DEAD;
-                            hpos[h].x = DEAD_X;
-                            hole_bm[h >> 5] &= ~(1u << (h & 31));
-                        }
+                        if (lane == 0) { cr[smin] = F_INF; near[smin] = (NearT)NEAR_DEAD; hole_bm[h >> 5] &= ~(1u << (h & 31)); }
                         n_e--;
                     }
-                    __threadfence_block();
+                    __threadfence_block();                  // (only shared-memory stores are pending here: the global ones follow the flag)
                     if (lane == 0) *s_done = k + 1;
                     MCL_PTIME(23)
+                    if (is_rec && lane == 0) hpos[hmin].x = DEAD_X;       // read by this warp's grid searches and after the pipeline only
                     // ---------------- fused histograms (off the sweep team's critical path)
                     if (hedge_next <= t_new) {
+                        flush_events();                     // the cursor moves: the events counted so far sit in the bin before it
                         while (hedge_next <= t_new) {
                             if (lane == 0 && p.hist_occ && hbin_next < p.hist.n_bins) {
                                 size_t q = (size_t)hrow * p.hist.n_bins + hbin_next;
@@ -1620,9 +1632,9 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                         }
                     }
                     t_cur = t_new;
-                    if (is_rec && lane == 0 && hist_on && p.hist_events) {
-                        const int b = h_mono ? (hbin_next - 1) : bin_of(t_cur);
-                        if (b >= 0 && b < p.hist.n_bins) atomicAdd(&p.hist_events[(size_t)hrow * p.hist.n_bins + b], 1ull);
+                    if (is_rec && hist_on && p.hist_events) {
+                        if (h_mono) ev_acc++;               // one atomic per bin, not per event
+                        else if (lane == 0) { const int b = bin_of(t_cur); if (b >= 0 && b < p.hist.n_bins) atomicAdd(&p.hist_events[(size_t)hrow * p.hist.n_bins + b], 1ull); }
                     }
                     k++;
 #ifdef MCL_PIPE_STATS
@@ -1631,6 +1643,7 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
                     MCL_PTIME(24)
                     MCL_PSTAT(0, 1)
                 }
+                flush_events();
                 if (lane == 0) {
                     s_pipe_d[0] = t_cur; s_pipe_d[1] = hedge_next; s_pipe_ll = esteps;
                     s_pipe_i[0] = hbin_next; s_pipe_i[1] = n_e; s_pipe_i[2] = k; s_pipe_i[3] = (int)es32;
