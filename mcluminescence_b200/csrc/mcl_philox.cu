@@ -380,8 +380,14 @@ __device__ __forceinline__ void seed_candidate_lists_impl(const Holes &H, const 
         const float lo_x = (ax > 0) ? (ax - 1) * H.w : -F_INF, hi_x = (ax < G - 1) ? (ax + 2) * H.w : F_INF;
         const float lo_y = (ay > 0) ? (ay - 1) * H.w : -F_INF, hi_y = (ay < G - 1) ? (ay + 2) * H.w : F_INF;
         const float lo_z = (az > 0) ? (az - 1) * H.w : -F_INF, hi_z = (az < G - 1) ? (az + 2) * H.w : F_INF;
-        for (int i = i0; i < i1; i++) {
-            const float x = ex[i], y = ey[i], z = ez[i];
+        // the cell's electrons are fetched 32 at a time (one round trip to L2 / HBM per cell instead of one per electron)
+        for (int ib = i0; ib < i1; ib += 32) {
+        const int mine_e = ib + lane;
+        float xl = 0.f, yl = 0.f, zl = 0.f;
+        if (mine_e < i1) { xl = ex[mine_e]; yl = ey[mine_e]; zl = ez[mine_e]; }
+        const int i_end = min(i1, ib + 32);
+        for (int i = ib; i < i_end; i++) {
+            const float x = __shfl_sync(0xffffffffu, xl, i - ib), y = __shfl_sync(0xffffffffu, yl, i - ib), z = __shfl_sync(0xffffffffu, zl, i - ib);
             float d2[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -412,6 +418,7 @@ __device__ __forceinline__ void seed_candidate_lists_impl(const Holes &H, const 
             const float bound = fminf(fminf(fminf(x - lo_x, hi_x - x), fminf(y - lo_y, hi_y - y)), fminf(z - lo_z, hi_z - z));
             if (od[KC - 1] <= bound * bound) store_lists(i, od, oj);
             else slow_lists(i);
+        }
         }
     }
 }
