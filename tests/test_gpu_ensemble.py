@@ -331,6 +331,11 @@ def test_pipelined_step_loop_changes_no_result(gpu):
     capped = workloads.c2(n_replicas=6, n_e=3000, n_bins=50)
     capped["segments"]["dt_cap"] = [0.25, 1e20]                 # most steps of the hold leg end at the cap: no event
     capped["max_steps"] = 30000
+    ramp_cb = workloads.c5(n_replicas=32)
+    # the kernel's (very conservative) test for "the conduction-band term cannot matter" compares it with the tunnelling rate at
+    # the box diagonal, alpha r = 910 here: E_cb = 35 eV passes it below ~600 K and fails it above, i.e. in the middle of this ramp
+    # (273 K -> 1073 K) the pipeline hands the leg back for good.  (basicTL12 ships E_cb = 1000 eV: never on.)
+    ramp_cb["replicas"]["E_cb"] = 35.0
     short = workloads.c2(n_replicas=6, n_e=3000, n_bins=50)
     short["max_steps"] = 700                                    # MCL_ERR_STEPS in the middle of the first leg
     jobs = [("c2, 512 threads", workloads.c2(n_replicas=12), None),
@@ -340,7 +345,11 @@ def test_pipelined_step_loop_changes_no_result(gpu):
             # conduction-band channel on (every clock takes the 4-SFU form); the boxes run nearly empty, so the legs end in order
             ("c2 conduction band", workloads.c2(n_replicas=8, n_e=3000, n_bins=50, physics_overrides=["physics_fp.E_cb=1.5"]), 256),
             ("c2 conduction band + two channels", workloads.c2(n_replicas=8, n_e=3000, n_bins=50, physics_overrides=["physics_fp.E_cb=1.5"] + two), 128),
-            ("c2 step cap", capped, 256), ("c2 out of steps", short, 256)]
+            ("c2 step cap", capped, 256), ("c2 out of steps", short, 256),
+            # ramps: identical channels and no conduction-band term -> the temperature is one uniform offset and the sweep team
+            # does not need it; with a finite E_cb the conduction-band term switches on during the ramp and the leg ends in order
+            ("c5 ramp, 128 threads", workloads.c5(n_replicas=48), 128), ("c5 ramp, 256 threads", workloads.c5(n_replicas=24), 256),
+            ("ramp into the conduction band", ramp_cb, 128)]
     took_pipeline = False
     for name, wl, nt in jobs:
         def go(pipe):
