@@ -1365,10 +1365,11 @@ __global__ void __launch_bounds__(NT, MINB) philox_kernel(const LaunchParams p, 
         //    (candidate list, else a grid search), re-evaluates the clocks of the thread that reported it and takes the
         //    minimum again.  No post-event scan, no sharing masks; each step's winner and waiting time are those of the
         //    loop in order (an exact FP32 tie at the minimum may go to the other slot).
-        //   sweep team:     sweep(k) -> wait until step k-2 is done (a flag) -> its best (clock, slot) per THREAD -> arrive FULL[k]
-        //   decision warp:  wait FULL[k] -> minimum of the team's entries -> winner retired while the sweep ran, stale, or
-        //                   written while the sweep ran?  re-evaluate that thread's chunks, again -> decision -> event ->
-        //                   step k done (flag) -> histograms
+        //   sweep team:     sweep(k) -> wait until step k-2 is done (a flag) -> every thread's best (clock, slot) and one row per warp
+        //                   (clock, slot, reporting lane) -> arrive FULL[k]
+        //   decision warp:  wait FULL[k] -> minimum of the rows -> winner retired while the sweep ran, stale, or written while
+        //                   the sweep ran?  re-evaluate the reporting thread's chunks (one per lane), rebuild that warp's row
+        //                   from its threads' entries, again -> decision -> event -> step k done (flag) -> histograms
         // Steps the pipeline cannot take (compaction due, last step of the leg, filling clock relevant) are handed back BEFORE
         // anything of them is applied; on the way out every stale electron is re-targeted and the sharing masks are rebuilt, so
         // the loop in order finds the state it would have produced itself.
