@@ -282,6 +282,7 @@ def main():
     counters, kernel_ms_native = [], []
     wall0 = time.perf_counter()
     e_first, e_last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = engine.launch_count()
     e_first.record(stream)
     for i in range(args.steps):
         ev[i][0].record(stream)
@@ -290,6 +291,7 @@ def main():
         counters.append(cnt)
         kernel_ms_native.append(kms)
     e_last.record(stream)
+    launches = engine.launch_count() - launches0          # this rank's kernels inside the timed region (every rank launches the same number)
     barrier()
     wall1 = time.perf_counter()
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
@@ -402,7 +404,7 @@ def main():
                        ("units_of_whole_job" if strong else "replicas_per_gpu_per_step"): int(args.replicas),
                        "l2": "working set per step (replica slabs) exceeds the 126 MB L2; fresh seed every step",
                        "rng": "philox4x32-10", "errors": errors},
-            "clocks": clocks, "gpu_launches": args.steps * world,
+            "clocks": clocks, "gpu_launches": launches * world,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roofline, "cpu_baseline": cpu,
         }

@@ -189,6 +189,10 @@ int mcl_device_peaks(mcl_peaks *out);
  * tests/test_gpu_philox.py pins the small-waiting-time tail with it. */
 int mcl_debug_exp_draws(const uint32_t *words, int32_t n, float *neg_lg2_u, float *lg2_of_that);
 
+/* Kernels this library has launched in this process so far (replay, block and one-warp kernels; the roofline
+ * microbenchmarks of mcl_device_peaks are not counted).  bench.py reads it around its timed region for `gpu_launches`. */
+int64_t mcl_launch_count(void);
+
 const char *mcl_last_error(void);
 int mcl_abi_version(void);
 

@@ -15,6 +15,7 @@ ABI_VERSION = 1
 EXPORTS = (
     "mcl_abi_version", "mcl_last_error", "mcl_workspace_bytes", "mcl_run", "mcl_run_host",
     "mcl_device_peaks", "mcl_objective", "mcl_release_scratch", "mcl_debug_exp_draws", "mcl_objective_last_kernel_ms",
+    "mcl_launch_count",
 )
 
 
@@ -101,6 +102,8 @@ def load():
     L.mcl_run.argtypes = [C.POINTER(RunArgs)]
     L.mcl_run_host.restype = C.c_int
     L.mcl_run_host.argtypes = [C.POINTER(RunArgs)]
+    L.mcl_launch_count.restype = C.c_int64
+    L.mcl_launch_count.argtypes = []
     L.mcl_device_peaks.restype = C.c_int
     L.mcl_device_peaks.argtypes = [C.POINTER(Peaks)]
     if hasattr(L, "mcl_objective"):

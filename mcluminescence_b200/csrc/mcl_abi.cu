@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <algorithm>
+#include <atomic>
 #include <vector>
 #include "mcl_common.cuh"
 
@@ -19,6 +20,8 @@ void set_error(const char *fmt, ...)
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<int64_t> g_launches{0};      // kernels launched by this process (mcl_launch_count)
 
 struct Layout {
     size_t off_rep, off_seg, off_obs, off_grp, off_order, off_slabs, total;
@@ -230,11 +233,11 @@ static int run_device(const mcl_run_args *a, cudaEvent_t ev0 = nullptr, cudaEven
     }
     if (ev0) cudaEventRecord(ev0, st);
     cudaError_t e = cudaSuccess;
-    if (a->mode == MCL_MODE_REPLAY) e = launch_replay(p, st);
+    if (a->mode == MCL_MODE_REPLAY) { e = launch_replay(p, st); g_launches++; }
     else {
         for (const auto &c : L.small_classes)
-            if (e == cudaSuccess) e = launch_smallbox(p, order_dev + c.begin, c.end - c.begin, c.hcap, st);
-        if (e == cudaSuccess && !L.big.empty()) e = launch_philox(p, st, 0);
+            if (e == cudaSuccess) { e = launch_smallbox(p, order_dev + c.begin, c.end - c.begin, c.hcap, st); g_launches++; }
+        if (e == cudaSuccess && !L.big.empty()) { e = launch_philox(p, st, 0); g_launches++; }
     }
     if (ev1) cudaEventRecord(ev1, st);
     if (e != cudaSuccess) { set_error("kernel launch: %s", cudaGetErrorString(e)); return MCL_ERR_CUDA; }
@@ -286,6 +289,7 @@ struct HostMirror {
 extern "C" {
 
 int mcl_abi_version(void) { return MCL_ABI_VERSION; }
+int64_t mcl_launch_count(void) { return g_launches.load(); }
 const char *mcl_last_error(void) { return g_err; }
 
 size_t mcl_workspace_bytes(const mcl_run_args *args)

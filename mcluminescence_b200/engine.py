@@ -274,6 +274,11 @@ def run_replay_chained(replicas: np.ndarray, segments: np.ndarray, max_steps: in
     return res
 
 
+def launch_count() -> int:
+    """Kernels libmcl_b200.so has launched in this process so far (bench.py's `gpu_launches`)."""
+    return int(_native.load().mcl_launch_count())
+
+
 def device_peaks() -> Dict[str, float]:
     """Measured issue-rate peaks of the current device (for the roofline denominators)."""
     _torch()
