@@ -66,6 +66,8 @@ __device__ __forceinline__ void set4(int (&a)[4], int k, int v)
 
 // Nearest alive hole of (x, y, z) among slots [0, n_hs): (squared distance, slot), ties to the smaller slot; slot = -1 when
 // no hole is alive.  WANT_FREE also returns the lowest dead slot (n_hs if none) for a fill.  All lanes get the results.
+// The arrays are padded to a multiple of 128 slots and every slot at or beyond n_hs reads as dead (x = 1e30), so the pass
+// needs neither index clamps nor bound predicates: three loads, six FP32 operations and the running minimum per hole.
 template <bool WANT_FREE>
 __device__ __forceinline__ void sb_search(const float *__restrict__ hx, const float *__restrict__ hy, const float *__restrict__ hz,
                                           int n_hs, float x, float y, float z, int lane, float &d2_out, int &slot_out, int &free_out)
@@ -75,24 +77,21 @@ __device__ __forceinline__ void sb_search(const float *__restrict__ hx, const fl
     for (int j0 = lane; j0 < n_hs; j0 += 128) {
         float hxv[4], hyv[4], hzv[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int jc = min(j0 + 32 * u, n_hs - 1);          // (clamped: a repeated slot never beats itself)
-            hxv[u] = hx[jc]; hyv[u] = hy[jc]; hzv[u] = hz[jc];
-        }
+        for (int u = 0; u < 4; u++) { hxv[u] = hx[j0 + 32 * u]; hyv[u] = hy[j0 + 32 * u]; hzv[u] = hz[j0 + 32 * u]; }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int j = j0 + 32 * u;
             const float dx = x - hxv[u], dy = y - hyv[u], dz = z - hzv[u];
             const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));   // a dead hole (x = 1e30) gives +inf
-            if (j < n_hs && d2 < bd) { bd = d2; bj = j; }
-            if (WANT_FREE && j < n_hs && hxv[u] > 0.5f * DEAD_X && j < fd) fd = j;
+            if (d2 < bd) { bd = d2; bj = j; }
+            if (WANT_FREE && hxv[u] > 0.5f * DEAD_X && j < fd) fd = j;       // (the padding is dead: the minimum is <= n_hs)
         }
     }
     const uint32_t m = warp_min_u32(__float_as_uint(bd));           // d2 >= 0: unsigned order is float order
     const uint32_t s = warp_min_u32(__float_as_uint(bd) == m && bd < F_INF ? (uint32_t)bj : 0x7fffffffu);
     d2_out = __uint_as_float(m);
     slot_out = s == 0x7fffffffu ? -1 : (int)s;
-    if (WANT_FREE) { const uint32_t f = warp_min_u32((uint32_t)fd); free_out = f == 0x7fffffffu ? n_hs : (int)f; }
+    if (WANT_FREE) { const uint32_t f = warp_min_u32((uint32_t)fd); free_out = min((int)f, n_hs); }
 }
 
 template <bool TRACE>
@@ -123,6 +122,9 @@ __global__ void __launch_bounds__(32, 20) smallbox_kernel(const LaunchParams p, 
     for (int k = 0; k < 4; k++) { c[k] = F_INF; nh[k] = -1; px[k] = py[k] = pz[k] = 0.f; birth[k] = lane + 32 * k; }
     int next_birth = rp.n_e0;
 
+    // every slot that holds no hole reads as dead (hcap is a multiple of 128: a search pass never needs a bound check)
+    for (int j = lane; j < hcap; j += 32) { hx[j] = DEAD_X; hy[j] = 0.f; hz[j] = 0.f; }
+    __syncwarp();
     if (status == MCL_OK) {
         // ---------------- Box.seed (engine.py:124-129): holes in generation order, electrons slot i = electron i
         for (int j = lane; j < n_hs; j += 32) {
@@ -405,6 +407,7 @@ cudaError_t launch_smallbox(const LaunchParams &p, const int *order_dev, int cou
 {
     if (count <= 0) return cudaSuccess;
     const RoundKeys K = make_round_keys(p.seed);
+    hcap = (hcap + 127) & ~127;                          // padded with dead slots: the search pass runs four loads deep without bound checks
     const size_t smem = sizeof(float) * 3 * (size_t)hcap;
     const bool trace = p.event || p.n_e || p.t;
     cudaError_t e;
