@@ -152,6 +152,43 @@ def test_c5_bench_instantiation_matches_oracle(gpu):
     print(f"C5 bench shape: worst n(T) deviation {worst:.2f} sigma")
 
 
+def test_pipelined_two_channel_and_ramp_match_oracle(gpu):
+    """The pipelined step loop against the oracle DIRECTLY (its equality with the loop in order is tested in
+    test_gpu_ensemble.py) on the two forms the bench shapes do not reach: two distinct tunnelling channels (hold + optical
+    readout, 4000-electron boxes => 128-thread CTAs, one Philox call per slot pair, per-electron selector), and a ramp
+    (4000 electrons, 2 degC/s: the sweep team's clocks carry no temperature, the decision warp adds the prefactor)."""
+    from mcluminescence_b200 import engine, workloads
+    from oracle import mcl_oracle as mo
+    R_g, R_o = 192, 32
+    two = workloads.c2(n_replicas=R_g, n_e=4000, n_bins=200, physics_overrides=["physics_fp.E_loc_2=1.0", "physics_fp.Retrap=0.3"])
+    ramp = workloads.c5(n_replicas=R_g, n_bins=200)
+    for k in ("N_e", "n_e0"):
+        ramp["replicas"][k] = 4000
+    ramp["replicas"]["n_h0"] = int(4000 * 1.2 ** 3)
+    ramp["replicas"]["side"] = ramp["replicas"]["side"] * (4000 / 2000) ** (1.0 / 3.0)          # same hole density as C5
+    ramp["segments"]["T_rate"] = 2.0
+    ramp["segments"]["duration"] = 400.0
+    ramp["segments"]["dt_cap"] = 0.5
+    for what, wl, coarse in (("two channels, pipelined", two, 20), ("ramp, pipelined", ramp, 10)):
+        with env(MCL_PHILOX_NT=128):
+            out = engine.run_replicas(wl["replicas"], wl["segments"], wl["max_steps"], seed=1777, hist=wl["hist"], trace=False, sync=True)
+            out.raise_on_error()
+            with env(MCL_PHILOX_PIPE=0):
+                inorder = engine.run_replicas(wl["replicas"][:32], wl["segments"], wl["max_steps"], seed=1777, hist=wl["hist"], trace=False, sync=True)
+        assert np.array_equal(inorder.steps_used, out.steps_used[:32]) and np.array_equal(inorder.esteps, out.esteps[:32]), what
+        ref = mo.run(wl["replicas"][:R_o], wl["segments"], wl["max_steps"], seed=91, parallel=True)
+        assert ref.rc == 0
+        _, _, _, worst = compare_with_oracle(wl, out, ref, R_g, what, coarse=coarse)
+        fin_g, fin_o = out.final_n_e.astype(float), ref.final_n_e.astype(float)
+        se = np.sqrt(fin_g.var(ddof=1) / R_g + fin_o.var(ddof=1) / R_o)
+        assert abs(fin_g.mean() - fin_o.mean()) <= Z * se + 0.5, (what, fin_g.mean(), fin_o.mean(), se)
+        es_g, es_o = out.esteps.astype(float), ref.esteps.astype(float)
+        se = np.sqrt(es_g.var(ddof=1) / R_g + es_o.var(ddof=1) / R_o)
+        assert abs(es_g.mean() - es_o.mean()) <= Z * se, (what, es_g.mean(), es_o.mean(), se)
+        assert int(out.steps_used.min()) > 500, what              # long enough to have run pipelined
+        print(f"{what}: worst n(t) deviation {worst:.2f} sigma; final n_e GPU {fin_g.mean():.1f} oracle {fin_o.mean():.1f}")
+
+
 def test_c3_dose_then_tl_matches_oracle(gpu):
     """BASELINE config 3: irradiation from EMPTY traps in the simulate protocol (`dose_rate` != 0: fills, stale
     incremental cache, the h+1 re-scan -- simulate.py:42,58,70-73, engine.py:133-175), then a TL ramp on the same box
